@@ -1,0 +1,164 @@
+// ab_internal.h -- shared host-side declarations of the B200 tensor backend (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/alchemy_b200.h"
+
+#define AB_MAX_LIMBS 8
+#define AB_MAX_AXES 12
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: every ABI entry is `return guard([&]{ ... });`
+void ab_set_error(const std::string &msg);
+struct ab_error {
+    int code;
+    std::string msg;
+};
+#define AB_CHECK_CUDA(expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            throw ab_error{AB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)};      \
+    } while (0)
+#define AB_REQUIRE(cond, code, msg)                                                               \
+    do {                                                                                          \
+        if (!(cond)) throw ab_error{(code), (msg)};                                               \
+    } while (0)
+
+template <class F>
+static inline int ab_guard(F &&f) {
+    try {
+        f();
+        return AB_OK;
+    } catch (const ab_error &e) {
+        ab_set_error(e.msg);
+        return e.code;
+    } catch (const std::exception &e) {
+        ab_set_error(e.what());
+        return AB_ERR_ARG;
+    } catch (...) {
+        ab_set_error("unknown failure");
+        return AB_ERR_ARG;
+    }
+}
+
+void ab_count_launch(uint64_t n = 1);
+void ab_check_launch(const char *what);   // cudaGetLastError after a launch; throws ab_error
+
+// ---------------------------------------------------------------------------------------------
+// host number theory (ab_plan.cpp)
+namespace abh {
+uint64_t mulmod(uint64_t a, uint64_t b, uint64_t q);
+uint64_t powmod(uint64_t b, uint64_t e, uint64_t q);
+uint64_t invmod(uint64_t a, uint64_t q);   // q prime
+bool is_prime(uint64_t q);
+uint64_t smallest_generator(uint64_t q);
+int64_t ipow(int64_t b, int e);
+int64_t digit_rev(int p, int e, int64_t j);
+static inline uint32_t shoup(uint64_t w, uint64_t q) { return (uint32_t)((w << 32) / q); }
+}   // namespace abh
+
+// ---------------------------------------------------------------------------------------------
+// device-side parameter blocks (plain structs passed by value to kernels)
+struct uint2_ {
+    uint32_t x, y;
+};   // (w, floor(w*2^32/q)) Shoup pair; same layout as CUDA uint2
+
+struct AbLimbDev {
+    uint32_t q;
+    uint32_t ninv, ninv_s;       // pow2 path: n^-1 (Shoup pair) folded into the last inverse stage
+    uint64_t mu;                 // floor(2^64 / q) for Barrett reduction of 62-bit products
+    const uint2_ *tw_fwd;        // pow2 path: merged negacyclic twiddles, heap order [2^s + l]
+    const uint2_ *tw_inv;        // pow2 path: their inverses
+    const uint2_ *gen_fwd;       // generic path: per-limb table block (matrices, twiddles)
+    const uint2_ *gen_inv;
+    const uint2_ *g_crt;         // g at every CRT row (Shoup pairs), n entries
+    const uint2_ *ginv_crt;
+    uint32_t pinv[AB_MAX_AXES];  // p^-1 mod q per axis (divG)
+    uint32_t pinv_s[AB_MAX_AXES];
+};
+
+// one step of the generic mixed-radix transform (device array, shared by all limbs).
+// Work item v of a step: tb = v / estride, off = v % estride, base = tb*P*estride + off; its P
+// elements sit at base + k*estride.
+struct AbGenStep {
+    int32_t kind;       // 0 = dense PxP matvec, scale row = tb % h (CRT_p steps)
+                        // 2 = dense PxP matvec, scale row = off / sdiv (DFT_p stages)
+                        // 1 = radix-2 butterfly stage, twiddle row = off / sdiv
+    int32_t P;          // vector length (p-1 for CRT_p, p for DFT_p, 2 for radix-2)
+    int32_t estride;    // distance between the P elements of a work item
+    int32_t h;          // kind 0: p^(e-1); kinds 1,2: sub-transform size (rows of the twiddle table)
+    int32_t sdiv;       // kinds 1,2: twiddle row = off / sdiv
+    int32_t mode;       // 0 no scaling, 1 scale inputs, 2 scale outputs (table entry [row*P + k])
+    int32_t mat_off;    // offset (Shoup pairs) of the PxP matrix in the per-limb table block
+    int32_t sc_off;     // offset of the scale / twiddle table
+    int32_t nwork;      // work items in this step (n / P)
+    int32_t flags;      // kind 1 inverse: bit0 = multiply output 0 by table entry [h] (axis 2^-(e-1))
+};
+
+struct AbAxis {
+    int32_t p, e;
+    int64_t pp, phi, mp;    // p^e, phi(p^e), p^(e-1)
+    int64_t lts, rts;       // Kronecker sizes to the left / right
+};
+
+struct ab_plan {
+    int64_t m = 0, n = 0;
+    int32_t L = 0;
+    bool has_crt = false, pow2 = false;
+    int32_t logn = 0;
+    std::vector<AbAxis> axes;
+    std::vector<int64_t> q, root;
+    std::vector<AbLimbDev> limb;          // host copy of device parameter blocks
+    // generic transform program
+    std::vector<AbGenStep> steps_fwd, steps_inv;
+    AbGenStep *d_steps_fwd = nullptr, *d_steps_inv = nullptr;
+    std::vector<void *> owned;            // device allocations to free
+    int device = 0;
+    int sm_count = 148;
+    // host copies kept for tests / ext construction
+    std::vector<int64_t> mhat_inv;        // per limb
+};
+
+struct ab_ext {
+    const ab_plan *lo = nullptr, *hi = nullptr;
+    int64_t n_lo = 0, n_hi = 0, rel = 0;
+    int32_t *d_ext_pow = nullptr;      // [n_lo]   index into hi of pow/dec basis element j of lo
+    int32_t *d_pow_to_lo = nullptr;    // [n_hi]   inverse map (or -1)
+    int32_t *d_base_crt = nullptr;     // [n_hi]   CRT row of lo below CRT row of hi
+    int32_t *d_above_crt = nullptr;    // [n_lo][rel] CRT rows of hi above each row of lo
+    int32_t *d_coeff = nullptr;        // [rel][n_lo] coeffs index table
+    // embedDec is a signed gather: out_hi[j'] = sgn[j'] * in_lo[idx[j']]  (idx < 0: zero)
+    int32_t *d_edec_idx = nullptr;
+    int8_t *d_edec_sgn = nullptr;
+    // twaceCRT weights per limb: w[i'] = (mhat/mhat') * g'(i') / g(base(i'))  (Shoup pairs), [L][n_hi]
+    uint2_ *d_tw_weight = nullptr;
+    std::vector<void *> owned;
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (one .cu each)
+struct AbView {             // a batch of ring elements on the device
+    int64_t *y;
+    int64_t batch;
+    int32_t limb0, nlimbs;
+    int layout;
+};
+
+void ab_launch_crt_pow2(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st);
+bool ab_pow2_supported(const ab_plan *p);
+void ab_launch_crt_generic(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st);
+
+enum { AB_EW_MUL = 0, AB_EW_ADD = 1, AB_EW_SUB = 2, AB_EW_NEG = 3, AB_EW_SCALAR = 4, AB_EW_GCRT = 5, AB_EW_GINVCRT = 6 };
+void ab_launch_elementwise(const ab_plan *p, int op, const AbView &v, const int64_t *x, int64_t x_batch,
+                           const int64_t *scalars_host, cudaStream_t st);
+enum { AB_PR_L = 0, AB_PR_LINV = 1, AB_PR_GPOW = 2, AB_PR_GINVPOW = 3, AB_PR_GDEC = 4, AB_PR_GINVDEC = 5 };
+void ab_launch_prime_op(const ab_plan *p, int op, const AbView &v, cudaStream_t st);
+
+void ab_launch_gather(int64_t *out, const int64_t *in, const int32_t *idx, int64_t rows, int64_t n_out, int64_t n_in,
+                      cudaStream_t st);   // out[r][j] = idx[j] >= 0 ? in[r][idx[j]] : 0
+void ab_launch_layout(int64_t *out, const int64_t *in, int64_t batch, int32_t L, int64_t n, bool to_planar, cudaStream_t st);

@@ -1,0 +1,235 @@
+// ab_she.cpp -- ciphertext-level operations of Lol's SymmSHE as sequences of batched kernels.
+//
+// The reference reaches them at Crypto/Alchemy/Interpreter/Eval.hs:65-67 ((*) on CT), :130
+// (modSwitch), :133 (keySwitchQuadCirc), :134 (tunnel); PT2CT.hs:172-177 and :224-229 fix the order
+// in which they are chained.  Upstream performs them in Haskell on top of one-element Tensor calls
+// [RECALL]; here each is a handful of launches over the whole batch, with every intermediate in a
+// caller-supplied scratch buffer that is sized to stay L2-resident (the batch is processed in
+// chunks).  All polynomials are in the CRT basis, PLANAR layout: c[b][i][l][j].
+#include <algorithm>
+
+#include "ab_internal.h"
+#include "ab_kernels.h"
+
+static const int64_t kChunkBytes = 64ll << 20;   // scratch target per chunk: about half of the 126 MB L2
+
+static int64_t chunk_of(int64_t batch, int64_t bytes_per_item) {
+    int64_t c = kChunkBytes / std::max<int64_t>(1, bytes_per_item);
+    if (c < 1) c = 1;
+    return std::min(batch, c);
+}
+
+extern "C" int ab_ct_mul_dev(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, void *stream) {
+    return ab_guard([&] {
+        AB_REQUIRE(p && ((out3 && a2 && b2) || batch == 0), AB_ERR_ARG, "null argument");
+        AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan has no CRT tables");
+        AB_REQUIRE(batch >= 0 && nlimbs >= 1 && nlimbs <= p->L, AB_ERR_ARG, "bad batch or limb count");
+        ab_launch_ct_mul(p, out3, a2, b2, batch, nlimbs, (cudaStream_t)stream);
+    });
+}
+
+// ------------------------------------------------------------------------------------ modSwitch
+// rows = batch * npoly polynomials; per row: scratch for the dropped limb (n), the lifted limbs
+// ((from-1) n) and two ping-pong copies of the shrinking polynomial ((from-1) n each).
+static int64_t ms_row_words(const ab_plan *p, int32_t from, int32_t to) {
+    if (to >= from) return 0;
+    return p->n * (1 + 3 * (int64_t)(from - 1));
+}
+extern "C" int64_t ab_mod_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t npoly, int32_t from, int32_t to) {
+    if (!p || batch < 0 || npoly < 1) return -1;
+    const int64_t rw = ms_row_words(p, from, to);
+    return chunk_of(batch * npoly, rw * 8) * rw * 8;
+}
+static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, int64_t rows, int32_t from, int32_t to, int64_t *work, cudaStream_t st) {
+    const int64_t n = p->n;
+    if (to >= from) {
+        if (to == from) ab_launch_copy_rows(out, from * n, in, from * n, from * n, rows, st);
+        else ab_launch_rescale_up(p, out, to * n, in, from * n, rows, from, to, st);
+        return;
+    }
+    const int64_t rw = ms_row_words(p, from, to);
+    const int64_t chunk = chunk_of(rows, rw * 8);
+    for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+        const int64_t R = std::min(chunk, rows - r0);
+        int64_t *dropped = work, *lifted = dropped + R * n, *ping = lifted + R * (from - 1) * n, *pong = ping + R * (from - 1) * n;
+        const int64_t *cur = in + r0 * from * n;
+        int64_t cur_stride = from * n;
+        for (int32_t L = from; L > to; --L) {
+            const int32_t d = L - 1;
+            ab_launch_copy_rows(dropped, n, cur + (int64_t)d * n, cur_stride, n, R, st);
+            ab_crt_rows(p, dropped, R, d, true, st);
+            int32_t dst[AB_MAX_LIMBS];
+            for (int k = 0; k < d; ++k) dst[k] = k;
+            ab_launch_lift_reduce(p, lifted, (int64_t)d * n, dropped, n, R, d, dst, d, st);
+            ab_crt_dispatch(p, AbView{lifted, R, 0, d, AB_LAYOUT_PLANAR}, false, st);
+            int64_t scal[AB_MAX_LIMBS];
+            for (int k = 0; k < d; ++k) scal[k] = (int64_t)abh::invmod((uint64_t)p->q[d] % (uint64_t)p->q[k], (uint64_t)p->q[k]);
+            int64_t *dst_buf;
+            int64_t dst_stride;
+            if (d == to) { dst_buf = out + r0 * to * n; dst_stride = (int64_t)to * n; }
+            else { dst_buf = (cur == ping) ? pong : ping; dst_stride = (int64_t)d * n; }
+            ab_launch_sub_scale(p, dst_buf, dst_stride, cur, cur_stride, lifted, (int64_t)d * n, R, d, scal, st);
+            cur = dst_buf;
+            cur_stride = dst_stride;
+        }
+    }
+}
+extern "C" int ab_mod_switch_dev(const ab_plan *p, int64_t *out, const int64_t *in, int64_t batch, int32_t npoly, int32_t from, int32_t to,
+                                 void *work, void *stream) {
+    return ab_guard([&] {
+        AB_REQUIRE(p && ((out && in) || batch == 0), AB_ERR_ARG, "null argument");
+        AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan has no CRT tables");
+        AB_REQUIRE(batch >= 0 && npoly >= 1 && from >= 1 && to >= 1 && from <= p->L && to <= p->L, AB_ERR_ARG, "bad limb counts");
+        AB_REQUIRE(to >= from || work != nullptr, AB_ERR_ARG, "null scratch buffer");
+        mod_switch_rows(p, out, in, batch * npoly, from, to, (int64_t *)work, (cudaStream_t)stream);
+    });
+}
+
+// ------------------------------------------------------------------------------------ keySwitchQuadCirc
+static int64_t ks_item_words(const ab_plan *p, int32_t nlimbs, int32_t ndig) { return p->n * nlimbs * (1 + (int64_t)ndig); }
+extern "C" int64_t ab_key_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t nlimbs, int32_t base) {
+    const int32_t nd = ab_gadget_len(p, nlimbs, base);
+    if (nd < 0 || batch < 0) return -1;
+    const int64_t w = ks_item_words(p, nlimbs, nd);
+    return chunk_of(batch, w * 8) * w * 8;
+}
+extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int64_t *in3, const int64_t *hint, int64_t batch, int32_t nlimbs,
+                                      int32_t base, void *work, void *stream) {
+    return ab_guard([&] {
+        AB_REQUIRE(p && ((out2 && in3 && hint && work) || batch == 0), AB_ERR_ARG, "null argument");
+        AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan has no CRT tables");
+        const int32_t nd = ab_gadget_len(p, nlimbs, base);
+        AB_REQUIRE(nd > 0 && batch >= 0, AB_ERR_ARG, "bad limb count or gadget base");
+        cudaStream_t st = (cudaStream_t)stream;
+        const int64_t n = p->n, per = (int64_t)nlimbs * n;
+        const int64_t chunk = chunk_of(batch, ks_item_words(p, nlimbs, nd) * 8);
+        for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+            const int64_t B = std::min(chunk, batch - b0);
+            int64_t *c2 = (int64_t *)work, *dig = c2 + B * per;
+            const int64_t *in = in3 + b0 * 3 * per;
+            // c2 -> powerful basis -> gadget digits reduced into every limb -> back to CRT
+            ab_launch_copy_rows(c2, per, in + 2 * per, 3 * per, per, B, st);
+            ab_crt_dispatch(p, AbView{c2, B, 0, nlimbs, AB_LAYOUT_PLANAR}, true, st);
+            ab_launch_decompose(p, dig, c2, B, nlimbs, nlimbs, base, st);
+            ab_crt_dispatch(p, AbView{dig, B * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
+            // (c0, c1) + sum_d dig_d * hint_d
+            ab_launch_hint_ip(p, out2 + b0 * 2 * per, 2 * per, dig, (int64_t)nd * per, hint, in, 3 * per, false, B, nlimbs, nd, st);
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------ tunnel
+struct ab_tunnel {
+    const ab_plan *r = nullptr, *e = nullptr, *s = nullptr;
+    ab_ext *er = nullptr, *es = nullptr;
+    int64_t K = 0;                 // dimension of O_r' over O_e'
+    int32_t *d_pow = nullptr;      // [K][n_s] index into [n_r] of the powerful-basis source, -1 = zero
+    int32_t *d_dec = nullptr;      // same for the decoding basis
+    int8_t *d_dec_sgn = nullptr;   // [K][n_s]
+};
+
+extern "C" int ab_tunnel_create(ab_tunnel **out, const ab_plan *plan_r, const ab_plan *plan_e, const ab_plan *plan_s) {
+    ab_tunnel *t = nullptr;
+    int rc = ab_guard([&] {
+        AB_REQUIRE(out && plan_r && plan_e && plan_s, AB_ERR_ARG, "null argument");
+        AB_REQUIRE(plan_r->has_crt && plan_s->has_crt, AB_ERR_NO_ROOT, "r' and s' plans need CRT tables");
+        t = new ab_tunnel();
+        t->r = plan_r; t->e = plan_e; t->s = plan_s;
+        int rc2 = ab_ext_create(&t->er, plan_e, plan_r);
+        if (rc2 != AB_OK) throw ab_error{rc2, ab_last_error()};
+        rc2 = ab_ext_create(&t->es, plan_e, plan_s);
+        if (rc2 != AB_OK) throw ab_error{rc2, ab_last_error()};
+        t->K = t->er->rel;
+        const int64_t ne = plan_e->n, ns = plan_s->n, K = t->K;
+        // compose coeffs (r' -> K x e') with embed (e' -> s') into one gather table per basis
+        std::vector<int32_t> coeff(K * ne), pow_to_lo(ns), edec_idx(ns);
+        std::vector<int8_t> edec_sgn(ns);
+        AB_CHECK_CUDA(cudaMemcpy(coeff.data(), t->er->d_coeff, coeff.size() * 4, cudaMemcpyDeviceToHost));
+        AB_CHECK_CUDA(cudaMemcpy(pow_to_lo.data(), t->es->d_pow_to_lo, ns * 4, cudaMemcpyDeviceToHost));
+        AB_CHECK_CUDA(cudaMemcpy(edec_idx.data(), t->es->d_edec_idx, ns * 4, cudaMemcpyDeviceToHost));
+        AB_CHECK_CUDA(cudaMemcpy(edec_sgn.data(), t->es->d_edec_sgn, ns, cudaMemcpyDeviceToHost));
+        std::vector<int32_t> tp(K * ns), td(K * ns);
+        std::vector<int8_t> ts(K * ns);
+        for (int64_t k = 0; k < K; ++k)
+            for (int64_t j = 0; j < ns; ++j) {
+                tp[k * ns + j] = pow_to_lo[j] < 0 ? -1 : coeff[k * ne + pow_to_lo[j]];
+                td[k * ns + j] = edec_idx[j] < 0 ? -1 : coeff[k * ne + edec_idx[j]];
+                ts[k * ns + j] = edec_sgn[j];
+            }
+        AB_CHECK_CUDA(cudaMalloc((void **)&t->d_pow, tp.size() * 4));
+        AB_CHECK_CUDA(cudaMalloc((void **)&t->d_dec, td.size() * 4));
+        AB_CHECK_CUDA(cudaMalloc((void **)&t->d_dec_sgn, ts.size()));
+        AB_CHECK_CUDA(cudaMemcpy(t->d_pow, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice));
+        AB_CHECK_CUDA(cudaMemcpy(t->d_dec, td.data(), td.size() * 4, cudaMemcpyHostToDevice));
+        AB_CHECK_CUDA(cudaMemcpy(t->d_dec_sgn, ts.data(), ts.size(), cudaMemcpyHostToDevice));
+        *out = t;
+    });
+    if (rc != AB_OK && t) ab_tunnel_destroy(t);
+    return rc;
+}
+extern "C" void ab_tunnel_destroy(ab_tunnel *t) {
+    if (!t) return;
+    ab_ext_destroy(t->er);
+    ab_ext_destroy(t->es);
+    cudaFree(t->d_pow);
+    cudaFree(t->d_dec);
+    cudaFree(t->d_dec_sgn);
+    delete t;
+}
+
+// scratch per ciphertext: crtInv'd input 2 L n_r; decoding-basis copy of c0 L n_r; c0 parts and c1 parts
+// K L n_s each; digits K nd L n_s; the evalLin result L n_s
+static int64_t tn_item_words(const ab_tunnel *t, int32_t nlimbs, int32_t nd) {
+    return 3 * (int64_t)nlimbs * t->r->n + (int64_t)nlimbs * t->s->n * (t->K * (2 + nd) + 1);
+}
+extern "C" int64_t ab_tunnel_work_bytes(const ab_tunnel *t, int64_t batch, int32_t nlimbs, int32_t base) {
+    if (!t || batch < 0) return -1;
+    const int32_t nd = ab_gadget_len(t->s, nlimbs, base);
+    if (nd < 0) return -1;
+    const int64_t w = tn_item_words(t, nlimbs, nd);
+    return chunk_of(batch, w * 8) * w * 8;
+}
+
+extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t *in2_r, const int64_t *flin, const int64_t *hint, int64_t batch,
+                             int32_t nlimbs, int32_t base, void *work, void *stream) {
+    return ab_guard([&] {
+        AB_REQUIRE(t && ((out2_s && in2_r && flin && hint && work) || batch == 0), AB_ERR_ARG, "null argument");
+        const ab_plan *pr = t->r, *ps = t->s;
+        AB_REQUIRE(batch >= 0 && nlimbs >= 1 && nlimbs <= pr->L && nlimbs <= ps->L, AB_ERR_ARG, "bad limb count");
+        const int32_t nd = ab_gadget_len(ps, nlimbs, base);
+        AB_REQUIRE(nd > 0, AB_ERR_ARG, "bad gadget base");
+        for (int l = 0; l < nlimbs; ++l) AB_REQUIRE(pr->q[l] == ps->q[l], AB_ERR_ARG, "r' and s' plans must share their moduli");
+        cudaStream_t st = (cudaStream_t)stream;
+        const int64_t nr = pr->n, ns = ps->n, K = t->K;
+        const int64_t per_r = (int64_t)nlimbs * nr, per_s = (int64_t)nlimbs * ns;
+        const int64_t chunk = chunk_of(batch, tn_item_words(t, nlimbs, nd) * 8);
+        for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+            const int64_t B = std::min(chunk, batch - b0);
+            int64_t *cin = (int64_t *)work;          // [B][2][L][n_r]
+            int64_t *c0d = cin + B * 2 * per_r;      // [B][L][n_r]
+            int64_t *p0 = c0d + B * per_r;           // [B][K][L][n_s]
+            int64_t *p1 = p0 + B * K * per_s;        // [B][K][L][n_s]
+            int64_t *dig = p1 + B * K * per_s;       // [B][K][nd][L][n_s]
+            int64_t *lin = dig + B * K * nd * per_s; // [B][L][n_s]
+            int64_t *o = out2_s + b0 * 2 * per_s;
+            // (c0, c1) to the powerful basis of O_r'
+            ab_launch_copy_rows(cin, 2 * per_r, in2_r + b0 * 2 * per_r, 2 * per_r, 2 * per_r, B, st);
+            ab_crt_dispatch(pr, AbView{cin, B * 2, 0, nlimbs, AB_LAYOUT_PLANAR}, true, st);
+            // c0: decoding basis, split over E' (coeffsDec), embed each part into O_s' (embedDec), to CRT
+            ab_launch_copy_rows(c0d, per_r, cin, 2 * per_r, per_r, B, st);
+            ab_launch_prime_op(pr, AB_PR_LINV, AbView{c0d, B, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
+            ab_launch_tunnel_gather(ps, p0, c0d, per_r, nr, t->d_dec, t->d_dec_sgn, B, K, nlimbs, st);
+            ab_launch_prime_op(ps, AB_PR_L, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
+            ab_crt_dispatch(ps, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
+            // evalLin: c0' = sum_k p0_k * flin_k
+            ab_launch_lin_ip(ps, lin, per_s, p0, K * per_s, flin, B, nlimbs, (int32_t)K, st);
+            // c1: split over E' in the powerful basis (coeffsPow), embed (embedPow), decompose, reduce, CRT
+            ab_launch_tunnel_gather(ps, p1, cin + per_r, 2 * per_r, nr, t->d_pow, nullptr, B, K, nlimbs, st);
+            ab_launch_decompose(ps, dig, p1, B * K, nlimbs, nlimbs, base, st);
+            ab_crt_dispatch(ps, AbView{dig, B * K * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
+            // (c0'', c1'') = sum_{k,d} dig_{k,d} * hint_{k,d};  then c0'' += c0'
+            ab_launch_hint_ip(ps, o, 2 * per_s, dig, K * nd * per_s, hint, nullptr, 0, false, B, nlimbs, (int32_t)(K * nd), st);
+            ab_launch_add_rows(ps, o, 2 * per_s, lin, per_s, B, nlimbs, st);
+        }
+    });
+}
