@@ -4,5 +4,5 @@ Python here is the host-side mirror of the reference's operator interface (Lol `
 SymmSHE's ciphertext operations as called from Crypto/Alchemy/Interpreter/Eval.hs); all arithmetic
 runs in hand-written sm_100a CUDA kernels behind the C ABI of include/alchemy_b200.h.
 """
-from ._lib import AlchemyError, INTERLEAVED, PLANAR, lib  # noqa: F401
+from ._lib import AlchemyError, INTERLEAVED, PLANAR, check, lib  # noqa: F401
 from .tensor import GT, Ext, Plan  # noqa: F401

@@ -167,10 +167,25 @@ static void run_op(const ab_plan *p, int op, const AbView &v, cudaStream_t st) {
     }
 }
 
+// stream-ordered scratch from the device's default memory pool (kept warm: the release threshold is raised
+// once, so repeated host-entry calls do not pay cudaMalloc/cudaFree each time)
 struct DevBuf {
     int64_t *p = nullptr;
-    explicit DevBuf(size_t bytes) { AB_CHECK_CUDA(cudaMalloc((void **)&p, bytes ? bytes : 8)); }
-    ~DevBuf() { cudaFree(p); }
+    cudaStream_t st;
+    DevBuf(size_t bytes, cudaStream_t s) : st(s) {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        });
+        AB_CHECK_CUDA(cudaMallocAsync((void **)&p, bytes ? bytes : 8, st));
+    }
+    ~DevBuf() { cudaFreeAsync(p, st); }
     DevBuf(const DevBuf &) = delete;
 };
 
@@ -179,8 +194,8 @@ extern "C" int ab_tensor_op_host(const ab_plan *p, int op, int64_t *y_host, int6
         AB_REQUIRE(p && (y_host || batch == 0) && batch >= 0, AB_ERR_ARG, "bad arguments");
         if (batch == 0) return;
         const size_t bytes = (size_t)batch * p->L * p->n * sizeof(int64_t);
-        DevBuf d(bytes), t(layout == AB_LAYOUT_INTERLEAVED && p->L > 1 ? bytes : 0);
         cudaStream_t st = 0;
+        DevBuf d(bytes, st), t(layout == AB_LAYOUT_INTERLEAVED && p->L > 1 ? bytes : 0, st);
         AB_CHECK_CUDA(cudaMemcpyAsync(d.p, y_host, bytes, cudaMemcpyHostToDevice, st));
         if (layout == AB_LAYOUT_INTERLEAVED && p->L > 1) {
             // de-interleave once on the device so every kernel streams contiguous limbs
@@ -199,8 +214,8 @@ extern "C" int ab_mul_host(const ab_plan *p, int64_t *y_host, const int64_t *x_h
         AB_REQUIRE(p && ((y_host && x_host) || batch == 0) && batch >= 0, AB_ERR_ARG, "bad arguments");
         if (batch == 0) return;
         const size_t bytes = (size_t)batch * p->L * p->n * sizeof(int64_t);
-        DevBuf dy(bytes), dx(bytes);
         cudaStream_t st = 0;
+        DevBuf dy(bytes, st), dx(bytes, st);
         AB_CHECK_CUDA(cudaMemcpyAsync(dy.p, y_host, bytes, cudaMemcpyHostToDevice, st));
         AB_CHECK_CUDA(cudaMemcpyAsync(dx.p, x_host, bytes, cudaMemcpyHostToDevice, st));
         ab_launch_elementwise(p, AB_EW_MUL, AbView{dy.p, batch, 0, p->L, layout}, dx.p, batch, nullptr, st);
