@@ -1,0 +1,157 @@
+"""Tier-1 for the ciphertext-level entries (ab_ct_mul_dev, ab_mod_switch_dev, ab_key_switch_quad_dev,
+ab_tunnel_dev, ab_decompose_dev, ab_rescale_drop_dev): bit-exact against oracle/she_oracle.py, which
+computes the same operations definitionally through the powerful basis (run under gpurun: `pytest -m gpu`).
+Shapes follow the limb schedule of the reference's examples."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import she_oracle as S
+
+pytestmark = pytest.mark.gpu
+
+ARITH_Q = [268440577, 8392193, 1073750017]
+RLWR_Q = [1543651201, 689270401, 718099201, 720720001, 1556755201, 1567238401]
+TUNNEL_Q = [537264001, 539884801, 555609601, 560851201, 566092801]
+
+
+def dev(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def rand(rng, lead, moduli, n):
+    return np.stack([rng.integers(0, q, size=tuple(lead) + (n,), dtype=np.int64) for q in moduli], axis=-2)
+
+
+@pytest.mark.parametrize("m,moduli,base", [(32, [97, 193, 257], 0), (32, [97, 193, 257], 2), (45, [181, 541], 3),
+                                            (512, ARITH_Q[:2], 0), (20475, RLWR_Q[:3], 0), (11648, TUNNEL_Q[:1], 2)])
+def test_decompose_and_rescale(m, moduli, base):
+    import alchemy_b200 as ab
+    rng = np.random.default_rng(m + base)
+    plan = ab.Plan(m, moduli, crt=False)
+    x = rand(rng, (3,), moduli, plan.n)
+    x[0, :, 0] = [q - 1 for q in moduli]
+    x[0, :, 1] = [q // 2 for q in moduli]
+    x[0, :, 2] = [q // 2 + 1 for q in moduli]
+    x[0, :, 3] = 0
+    got = ab.GT.decompose(plan, dev(x), base=base).cpu().numpy()
+    assert (got == S.decompose(x, moduli, moduli, base)).all()
+    assert ab.GT.gadgetLen(plan, len(moduli), base) == S.gadget_len(moduli, base)
+    if len(moduli) > 1:
+        got = ab.GT.decompose(plan, dev(x), base=base, out_limbs=1).cpu().numpy()
+        assert (got == S.decompose(x, moduli, moduli[:1], base)).all()
+        for drop in range(len(moduli)):
+            got = ab.GT.rescaleDrop(plan, dev(x), drop=drop).cpu().numpy()
+            assert (got == S.rescale_drop(x, moduli, drop)).all()
+
+
+MULS = [  # (m, moduli, L_in, L_hint, L_out, base): the limb schedule of SURVEY.md B.3
+    (512, ARITH_Q, 2, 2, 1, 0),             # examples/Arithmetic.hs
+    (20475, RLWR_Q, 4, 5, 3, 0),            # HomomRLWR level 1
+    (20475, RLWR_Q, 3, 4, 2, 0),            # level 2
+    (20475, RLWR_Q, 2, 3, 1, 0),            # level 3
+    (20475, RLWR_Q, 1, 2, 1, 0),            # level 4
+    (36, [37, 73, 109], 2, 3, 1, 0),
+    (64, [193, 257, 449], 2, 2, 1, 4),      # BaseBGad on a product ring
+]
+
+
+@pytest.mark.parametrize("m,moduli,lin,lh,lout,base", MULS)
+def test_mul_keyswitch_pipeline(m, moduli, lin, lh, lout, base):
+    """PT2CT.hs:172-177: modSwitch . keySwitchQuad hint . modSwitch . (*) -- every stage against the oracle"""
+    import alchemy_b200 as ab
+    from alchemy_b200 import she
+    rng = np.random.default_rng(m + lin)
+    plan = ab.Plan(m, moduli)
+    n, B = plan.n, 3
+    a, b = rand(rng, (B, 2), moduli[:lin], n), rand(rng, (B, 2), moduli[:lin], n)
+    D = S.gadget_len(moduli[:lh], base)
+    hint = rand(rng, (D, 2), moduli[:lh], n)
+    c3 = she.ctMul(plan, dev(a), dev(b))
+    w3 = S.ct_mul(m, moduli[:lin], a, b)
+    assert (c3.cpu().numpy() == w3).all()
+    c3h = she.modSwitch(plan, c3, lh)
+    w3h = S.mod_switch(m, moduli, w3, lh)
+    assert (c3h.cpu().numpy() == w3h).all()
+    c2 = she.keySwitchQuadCirc(plan, c3h, dev(hint), base)
+    w2 = S.key_switch_quad(m, moduli, w3h, hint, base)
+    assert (c2.cpu().numpy() == w2).all()
+    out = she.modSwitch(plan, c2, lout)
+    want = S.mod_switch(m, moduli, w2, lout)
+    assert (out.cpu().numpy() == want).all()
+    # and the fused host call gives the same thing
+    assert (she.mulKeySwitch(plan, dev(a), dev(b), dev(hint), lh, lout, base).cpu().numpy() == want).all()
+
+
+@pytest.mark.parametrize("m,moduli,frm,to", [(512, ARITH_Q, 3, 1), (512, ARITH_Q, 1, 3), (20475, RLWR_Q, 6, 2), (20475, RLWR_Q, 5, 5),
+                                              (45, [181, 541, 631], 3, 2), (11648, TUNNEL_Q, 2, 1)])
+def test_mod_switch(m, moduli, frm, to):
+    import alchemy_b200 as ab
+    from alchemy_b200 import she
+    rng = np.random.default_rng(m + frm * 10 + to)
+    plan = ab.Plan(m, moduli)
+    c = rand(rng, (4, 2), moduli[:frm], plan.n)
+    c[0, :, :, 0] = np.array(moduli[:frm]) - 1
+    got = she.modSwitch(plan, dev(c), to).cpu().numpy()
+    assert (got == S.mod_switch(m, moduli, c, to)).all()
+
+
+TUNNELS = [  # (r', e', s', moduli, L, base)
+    (12, 4, 20, [61, 181, 241], 2, 0), (9, 3, 21, [127, 379], 2, 3), (45, 15, 15, [181, 541], 1, 2), (16, 16, 48, [97, 193], 2, 0),
+    (11648, 5824, 29120, TUNNEL_Q, 1, 2),        # examples/Tunnel.hs hop 1 -> 2 (BaseBGad 2, one limb)
+    (29120, 14560, 43680, RLWR_Q, 2, 0),         # HomomRLWR hop 2 (TrivGad), 2 of its limbs
+    (43680, 10920, 54600, RLWR_Q, 1, 0),         # hop 3: dim 4
+    (54600, 27300, 27300, RLWR_Q, 2, 0),         # hop 4: s' = e'
+    (27300, 6825, 20475, RLWR_Q, 1, 0),          # hop 5
+]
+
+
+@pytest.mark.parametrize("r,e,s,moduli,L,base", TUNNELS)
+def test_tunnel(r, e, s, moduli, L, base):
+    import alchemy_b200 as ab
+    from alchemy_b200 import she
+    rng = np.random.default_rng(r + s)
+    q = moduli[:L]
+    pr, ps = ab.Plan(r, q), ab.Plan(s, q)
+    pe = ab.Plan(e, q, crt=False)
+    tn = she.Tunnel(pr, pe, ps)
+    K = pr.n // pe.n
+    D = S.gadget_len(q, base)
+    B = 2
+    c = rand(rng, (B, 2), q, pr.n)
+    flin = rand(rng, (K,), q, ps.n)
+    hint = rand(rng, (K, D, 2), q, ps.n)
+    got = tn(dev(c), dev(flin), dev(hint), base).cpu().numpy()
+    want = S.tunnel(r, e, s, q, c, flin, hint, base)
+    assert (got == want).all()
+
+
+def test_full_size_roundtrip_properties():
+    """size-independent checks at a BASELINE-size batch: crtInv.crt = id, linearity of key switching in (c0,c1)"""
+    import torch
+
+    import alchemy_b200 as ab
+    from alchemy_b200 import she
+    m, moduli = 20475, RLWR_Q[:4]
+    plan = ab.Plan(m, moduli)
+    n, B = plan.n, 512
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = torch.stack([torch.randint(0, q, (B, n), dtype=torch.int64, device="cuda", generator=g) for q in moduli], dim=1)
+    y = x.clone()
+    ab.GT.crt(plan, y)
+    assert not torch.equal(x, y)
+    ab.GT.crtInv(plan, y)
+    assert torch.equal(x, y)
+    # key switch: out(c0 + d0, c1, c2) - out(c0, c1, c2) == d0 exactly
+    D = S.gadget_len(moduli, 0)
+    hint = torch.stack([torch.randint(0, q, (D, 2, n), dtype=torch.int64, device="cuda", generator=g) for q in moduli], dim=2)
+    c3 = torch.stack([torch.randint(0, q, (64, 3, n), dtype=torch.int64, device="cuda", generator=g) for q in moduli], dim=2)
+    d0 = torch.stack([torch.randint(0, q, (64, n), dtype=torch.int64, device="cuda", generator=g) for q in moduli], dim=1)
+    qv = torch.tensor(moduli, device="cuda")[None, :, None]
+    o1 = she.keySwitchQuadCirc(plan, c3, hint)
+    c3b = c3.clone()
+    c3b[:, 0] = (c3b[:, 0] + d0) % qv
+    o2 = she.keySwitchQuadCirc(plan, c3b, hint)
+    assert torch.equal((o2[:, 0] - o1[:, 0]) % qv, d0) and torch.equal(o2[:, 1], o1[:, 1])
