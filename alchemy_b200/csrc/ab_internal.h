@@ -68,12 +68,39 @@ struct uint2_ {
     uint32_t x, y;
 };   // (w, floor(w*2^32/q)) Shoup pair; same layout as CUDA uint2
 
+// ---------------------------------------------------------------------------------------------
+// power-of-two kernel geometry, shared by the table builder (ab_plan.cpp) and the kernels (ab_ntt_pow2.cu).
+// A transform of n = 2^logn points is cut into windows of `loge` butterfly stages held in registers;
+// window w starts at stage S(w) and skips its first LB0(w) stages (only the last window can overlap).
+// Twiddles are stored window-packed: for window w, entry k = 2^lb + ip - koff(w) of column `low` sits at
+//   base(w) + ((k/2) * 2^S + low) * 2 + (k & 1)        (uint2 units)
+// so that one 16-byte load per lane fetches two consecutive entries and lanes are contiguous.
+#if defined(__CUDACC__)
+#define AB_HD __host__ __device__
+#else
+#define AB_HD
+#endif
+AB_HD constexpr int ab_pow2_loge(int logn) { return logn == 5 ? 5 : logn == 6 ? 3 : logn <= 8 ? 4 : 5; }
+AB_HD constexpr int ab_pow2_nw(int logn, int loge) { return (logn + loge - 1) / loge; }
+AB_HD constexpr int ab_pow2_s(int logn, int loge, int w) { return (w * loge + loge <= logn) ? w * loge : logn - loge; }
+AB_HD constexpr int ab_pow2_lb0(int logn, int loge, int w) { return w * loge - ab_pow2_s(logn, loge, w); }
+AB_HD constexpr int ab_pow2_koff(int logn, int loge, int w) { return ab_pow2_lb0(logn, loge, w) == 0 ? 0 : (1 << ab_pow2_lb0(logn, loge, w)); }
+AB_HD constexpr int64_t ab_pow2_wsize(int logn, int loge, int w) {   // uint2 entries of window w
+    return (int64_t)((1 << loge) - ab_pow2_koff(logn, loge, w)) << ab_pow2_s(logn, loge, w);
+}
+AB_HD constexpr int64_t ab_pow2_base(int logn, int loge, int w) {
+    int64_t b = 0;
+    for (int i = 0; i < w; ++i) b += ab_pow2_wsize(logn, loge, i);
+    return b;
+}
+
 struct AbLimbDev {
     uint32_t q;
     uint32_t ninv, ninv_s;       // pow2 path: n^-1 (Shoup pair) folded into the last inverse stage
     uint64_t mu;                 // floor(2^64 / q) for Barrett reduction of 62-bit products
-    const uint2_ *tw_fwd;        // pow2 path: merged negacyclic twiddles, heap order [2^s + l]
+    const uint2_ *tw_fwd;        // pow2 path: merged negacyclic twiddles, window-packed (see above)
     const uint2_ *tw_inv;        // pow2 path: their inverses
+    uint2_ tw0_fwd[32], tw0_inv[32];   // host copies of window 0 (same for every thread): passed as kernel constants
     const uint2_ *gen_fwd;       // generic path: per-limb table block (matrices, twiddles)
     const uint2_ *gen_inv;
     const uint2_ *g_crt;         // g at every CRT row (Shoup pairs), n entries

@@ -11,21 +11,30 @@
 // The log2(n) stages are cut into windows of LOGE stages; inside a window every butterfly is
 // register-to-register, between windows the residues are transposed through shared memory
 // (uint32, padded 33/32 against bank conflicts), in place.  With E = 32 the first two windows
-// touch only the 1024-element block owned by one warp, so they need __syncwarp only; a transform
-// of n <= 1024 never executes a CTA barrier and n = 32768 executes exactly one.
-// HBM traffic is one 16-byte-vector read and one coalesced write of the int64 residues: 16 n
-// bytes per transform, the algorithmic minimum.  Twiddles (Shoup pairs) come from L1/L2.
+// touch only the 1024-element block owned by one warp, so they need __syncwarp only.
+//
+// Memory pipeline (forward, n = 32768, where only one CTA fits an SM): CTAs are persistent.  As soon as every thread has pulled the
+// inputs of the last window out of shared memory, the buffer is dead, and the low 32-bit halves of the
+// NEXT transform's int64 residues are streamed into it with 4-byte cp.async (LDGSTS) while the last
+// window's butterflies run and its results are stored: HBM reads, HBM writes and arithmetic overlap
+// inside one CTA even at n = 32768 where only one CTA fits an SM.
+// HBM traffic is one read and one write of the int64 residues: 16 n bytes per transform, the
+// algorithmic minimum.  Twiddles (Shoup pairs) are window-packed so one 16-byte load fetches two;
+// window 0's 31 twiddles are the same for every thread and travel as kernel constants.
 #include "ab_internal.h"
+#include <utility>
+
 #include "ab_modarith.cuh"
 
 struct Pow2Limb {
     uint32_t q, ninv, ninv_s, pad;
-    const uint2 *tw;
+    const uint2 *tw;          // window-packed table (forward or inverse)
+    uint2 tw0[32];            // window 0, entry k = 2^lb + ip
 };
 struct Pow2Args {
     Pow2Limb limb[AB_MAX_LIMBS];
     int32_t nlimbs;
-    int64_t ntrans;
+    int64_t batch;            // ring elements; transform (b, limb) lives at y + (b * nlimbs + limb) * N
 };
 
 template <bool LAZY>
@@ -61,77 +70,117 @@ struct Pow2Cfg {
     static constexpr int TPC = (T >= 128) ? 1 : 128 / T;
     static constexpr int THREADS = T * TPC;
     static constexpr int PADN = N + (N >> 5);
-    static constexpr int NW = (LOGN + LOGE - 1) / LOGE;
+    static constexpr int NW = ab_pow2_nw(LOGN, LOGE);
     static constexpr int G = (T < 32) ? T : 32;          // lanes of one warp working on one transform
     static constexpr int MINB = (1024 / THREADS) > 0 ? (1024 / THREADS) : 1;
-    __host__ __device__ static constexpr int win_start(int w) { return (w * LOGE + LOGE <= LOGN) ? w * LOGE : LOGN - LOGE; }
-    __host__ __device__ static constexpr int win_lb0(int w) { return w * LOGE - win_start(w); }
+    // persistent + cp.async prefetch pays only where a single CTA fits an SM (measured on B200: n = 32768)
+    static constexpr bool PIPE = (LOGN >= 15);
 };
 
 __device__ __forceinline__ int phys(int a) { return a + (a >> 5); }
 
-template <int LOGE, int S, int LB0, bool LAZY>
-__device__ __forceinline__ void fwd_window(uint32_t (&x)[1 << LOGE], const uint2 *__restrict__ tw, int low, uint32_t q) {
-#pragma unroll
-    for (int lb = LB0; lb < LOGE; ++lb) {
-        const uint2 *t = tw + (1 << (S + lb)) + low;
-#pragma unroll
-        for (int ip = 0; ip < (1 << lb); ++ip) {
-            const uint2 w = __ldg(t + (ip << S));
-#pragma unroll
-            for (int hi = 0; hi < (1 << (LOGE - 1 - lb)); ++hi) {
-                const int i = ip + (hi << (lb + 1));
-                bf_fwd<LAZY>(x[i], x[i | (1 << lb)], w, q);
-            }
-        }
-    }
+// compile-time loops: the register array x[] must only ever be indexed by constants (a loop the compiler
+// declines to unroll would push it to local memory)
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    static_for_impl(f, std::make_integer_sequence<int, N>{});
 }
 
-template <int LOGE, int S, int LB0, bool LAZY>
-__device__ __forceinline__ void inv_window(uint32_t (&x)[1 << LOGE], const uint2 *__restrict__ tw, int low, uint32_t q,
-                                           uint32_t ninv, uint32_t ninv_s) {
-#pragma unroll
-    for (int lb = LOGE - 1; lb >= LB0; --lb) {
-        const uint2 *t = tw + (1 << (S + lb)) + low;
-#pragma unroll
-        for (int ip = 0; ip < (1 << lb); ++ip) {
-            const uint2 w = __ldg(t + (ip << S));
-#pragma unroll
-            for (int hi = 0; hi < (1 << (LOGE - 1 - lb)); ++hi) {
-                const int i = ip + (hi << (lb + 1));
+// twiddle k of this thread's column: window 0 from kernel constants (CTA-uniform), later windows from the
+// packed table, two entries per 16-byte load
+template <int W, int S, int K>
+__device__ __forceinline__ uint2 tw_get(const Pow2Limb &lp, const uint4 *tp, uint4 &pr, bool first_of_stage) {
+    if (W == 0) return lp.tw0[K];
+    if ((K & 1) == 0 || first_of_stage) pr = __ldg(tp + ((int64_t)(K >> 1) << S));
+    return (K & 1) ? make_uint2(pr.z, pr.w) : make_uint2(pr.x, pr.y);
+}
+
+template <int LOGE, int W, int S, int LB0, bool LAZY>
+__device__ __forceinline__ void fwd_window(uint32_t (&x)[1 << LOGE], const Pow2Limb &lp, const uint2 *__restrict__ tw, int64_t base,
+                                           int low, uint32_t q) {
+    constexpr int KOFF = (LB0 == 0) ? 0 : (1 << LB0);
+    const uint4 *tp = reinterpret_cast<const uint4 *>(tw + base) + low;
+    uint4 pr = make_uint4(0, 0, 0, 0);
+    static_for<(LOGE > LB0 ? LOGE - LB0 : 0)>([&](auto LBI) {
+        constexpr int lb = LB0 + decltype(LBI)::value;
+        static_for<(1 << lb)>([&](auto IP) {
+            constexpr int ip = decltype(IP)::value, k = (1 << lb) + ip - KOFF;
+            const uint2 w = tw_get<W, S, k>(lp, tp, pr, ip == 0);
+            static_for<(1 << (LOGE - 1 - lb))>([&](auto HI) {
+                constexpr int i = ip + (decltype(HI)::value << (lb + 1));
+                bf_fwd<LAZY>(x[i], x[i | (1 << lb)], w, q);
+            });
+        });
+    });
+}
+
+template <int LOGE, int W, int S, int LB0, bool LAZY>
+__device__ __forceinline__ void inv_window(uint32_t (&x)[1 << LOGE], const Pow2Limb &lp, const uint2 *__restrict__ tw, int64_t base,
+                                           int low, uint32_t q) {
+    constexpr int KOFF = (LB0 == 0) ? 0 : (1 << LB0);
+    const uint4 *tp = reinterpret_cast<const uint4 *>(tw + base) + low;
+    uint4 pr = make_uint4(0, 0, 0, 0);
+    static_for<(LOGE > LB0 ? LOGE - LB0 : 0)>([&](auto LBI) {
+        constexpr int lb = LOGE - 1 - decltype(LBI)::value;
+        static_for<(1 << lb)>([&](auto IP) {
+            constexpr int ip = decltype(IP)::value, k = (1 << lb) + ip - KOFF;
+            const uint2 w = tw_get<W, S, k>(lp, tp, pr, ip == 0);
+            static_for<(1 << (LOGE - 1 - lb))>([&](auto HI) {
+                constexpr int i = ip + (decltype(HI)::value << (lb + 1));
                 if (S + lb == 0) {
                     // last stage of the inverse: fold n^-1 in (tw[1] already carries it for the lower output)
-                    uint32_t X = x[i], Y = x[i | 1];
+                    const uint32_t X = x[i], Y = x[i | 1];
                     if (LAZY) {
-                        x[i] = ab_shoup_lazy(X + Y, ninv, ninv_s, q);
+                        x[i] = ab_shoup_lazy(X + Y, lp.ninv, lp.ninv_s, q);
                         x[i | 1] = ab_shoup_lazy(X - Y + 2 * q, w.x, w.y, q);
                     } else {
-                        x[i] = ab_shoup(ab_addmod(X, Y, q), ninv, ninv_s, q);
+                        x[i] = ab_shoup(ab_addmod(X, Y, q), lp.ninv, lp.ninv_s, q);
                         x[i | 1] = ab_shoup(ab_submod(X, Y, q), w.x, w.y, q);
                     }
                 } else {
                     bf_inv<LAZY>(x[i], x[i | (1 << lb)], w, q);
                 }
-            }
-        }
-    }
+            });
+        });
+    });
 }
 
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// window dispatch: the window parameters must be template arguments (w is a constant after unrolling)
+#define AB_FW(W) fwd_window<LOGE, W, ab_pow2_s(LOGN, LOGE, W), ab_pow2_lb0(LOGN, LOGE, W), LAZY>(x, lp, tw, ab_pow2_base(LOGN, LOGE, W), low, q)
+#define AB_IW(W) inv_window<LOGE, W, ab_pow2_s(LOGN, LOGE, W), ab_pow2_lb0(LOGN, LOGE, W), LAZY>(x, lp, tw, ab_pow2_base(LOGN, LOGE, W), low, q)
+#define AB_RUN_FWD_WINDOW(w) switch (w) { case 0: AB_FW(0); break; case 1: AB_FW(1); break; case 2: AB_FW(2); break; default: AB_FW(3); break; }
+#define AB_RUN_INV_WINDOW(w) switch (w) { case 0: AB_IW(0); break; case 1: AB_IW(1); break; case 2: AB_IW(2); break; default: AB_IW(3); break; }
+
+// ---------------------------------------------------------------------------------------------
+// forward, small transforms (several per CTA): load, transform, store
 template <int LOGN, int LOGE, bool LAZY>
 __global__ void __launch_bounds__(Pow2Cfg<LOGN, LOGE>::THREADS, Pow2Cfg<LOGN, LOGE>::MINB)
-k_crt_pow2_fwd(const Pow2Args args, int64_t *__restrict__ y) {
+k_crt_pow2_fwd(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
     using C = Pow2Cfg<LOGN, LOGE>;
     constexpr int E = C::E, T = C::T, G = C::G;
     extern __shared__ uint32_t smem[];
+    // grid = (groups of TPC ring elements, limbs): every slot of a CTA works in the same limb, so the limb's
+    // constants are CTA-uniform (constant-bank operands, no per-thread copies)
     const int tid = threadIdx.x, tl = tid & (T - 1), slot = tid / T;
-    int64_t trans = (int64_t)blockIdx.x * C::TPC + slot;
-    const bool active = trans < args.ntrans;
-    if (!active) trans = 0;
-    const Pow2Limb lp = args.limb[trans % args.nlimbs];
+    int64_t b = (int64_t)blockIdx.x * C::TPC + slot;
+    const bool active = b < args.batch;
+    if (!active) b = 0;
+    const Pow2Limb &lp = args.limb[blockIdx.y];
     const uint32_t q = lp.q;
     const uint2 *__restrict__ tw = lp.tw;
     uint32_t *sm = smem + slot * C::PADN;
-    int64_t *yp = y + trans * C::N;
+    int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * C::N;
 
     // coalesced 16-byte loads of the block this warp owns in window 0; narrow to uint32 in smem
     {
@@ -156,8 +205,7 @@ k_crt_pow2_fwd(const Pow2Args args, int64_t *__restrict__ y) {
     uint32_t x[E];
 #pragma unroll
     for (int w = 0; w < C::NW; ++w) {
-        // (compile-time after unrolling)
-        const int S = C::win_start(w), LB0 = C::win_lb0(w);
+        const int S = ab_pow2_s(LOGN, LOGE, w);
         const int low = tl & ((1 << S) - 1), high = tl >> S;
         const int base = low + (high << (S + LOGE));
         if (w > 0) {
@@ -165,12 +213,7 @@ k_crt_pow2_fwd(const Pow2Args args, int64_t *__restrict__ y) {
         }
 #pragma unroll
         for (int i = 0; i < E; ++i) x[i] = sm[phys(base + (i << S))];
-        switch (w) {   // window parameters must be template arguments
-            case 0: fwd_window<LOGE, C::win_start(0), C::win_lb0(0), LAZY>(x, tw, low, q); break;
-            case 1: fwd_window<LOGE, C::win_start(1), C::win_lb0(1), LAZY>(x, tw, low, q); break;
-            case 2: fwd_window<LOGE, C::win_start(2), C::win_lb0(2), LAZY>(x, tw, low, q); break;
-            default: fwd_window<LOGE, C::win_start(3), C::win_lb0(3), LAZY>(x, tw, low, q); break;
-        }
+        AB_RUN_FWD_WINDOW(w)
         if (w + 1 < C::NW) {
 #pragma unroll
             for (int i = 0; i < E; ++i) sm[phys(base + (i << S))] = x[i];
@@ -187,26 +230,89 @@ k_crt_pow2_fwd(const Pow2Args args, int64_t *__restrict__ y) {
     }
 }
 
+// forward, large transforms: persistent CTA, next transform prefetched with cp.async under the last window
 template <int LOGN, int LOGE, bool LAZY>
 __global__ void __launch_bounds__(Pow2Cfg<LOGN, LOGE>::THREADS, Pow2Cfg<LOGN, LOGE>::MINB)
-k_crt_pow2_inv(const Pow2Args args, int64_t *__restrict__ y) {
+k_crt_pow2_fwd_pipe(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
+    using C = Pow2Cfg<LOGN, LOGE>;
+    constexpr int E = C::E, G = C::G;
+    static_assert(C::TPC == 1 && G == 32, "pipelined kernel: one transform per CTA");
+    extern __shared__ uint32_t sm[];
+    const int tl = threadIdx.x;
+    const int wb = tl / G, lg = tl % G;
+
+    // low halves of the int64 residues of the 1024-element block this warp owns in window 0
+    const Pow2Limb &lp = args.limb[blockIdx.y];
+    const uint32_t q = lp.q;
+    const uint2 *__restrict__ tw = lp.tw;
+    auto prefetch = [&](int64_t b) {
+        const int64_t *src = y + (b * args.nlimbs + blockIdx.y) * C::N + wb * G * E + lg;
+        uint32_t *dst = sm + wb * G * E + wb * E + lg;      // phys(wb*1024 + lg + j*32) = that + wb*32 + j
+#pragma unroll
+        for (int j = 0; j < E; ++j) cp_async4(dst + j * (G + 1), src + j * G);
+        cp_async_commit();
+    };
+
+    int64_t b = blockIdx.x;
+    if (b < args.batch) prefetch(b);
+    for (; b < args.batch; b += gridDim.x) {
+        int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * C::N;
+        cp_async_wait_all();
+        __syncwarp();
+        uint32_t x[E];
+#pragma unroll
+        for (int w = 0; w < C::NW; ++w) {
+            const int S = ab_pow2_s(LOGN, LOGE, w);
+            const int low = tl & ((1 << S) - 1), high = tl >> S;
+            const int base = low + (high << (S + LOGE));
+            if (w > 0) {
+                if (S <= 5) __syncwarp(); else __syncthreads();
+            }
+#pragma unroll
+            for (int i = 0; i < E; ++i) x[i] = sm[phys(base + (i << S))];
+            if (w + 1 == C::NW) {
+                // every thread holds its last-window inputs: the buffer is dead, refill it for the next transform
+                __syncthreads();
+                const int64_t next = b + gridDim.x;
+                if (next < args.batch) prefetch(next);
+            }
+            AB_RUN_FWD_WINDOW(w)
+            if (w + 1 < C::NW) {
+#pragma unroll
+                for (int i = 0; i < E; ++i) sm[phys(base + (i << S))] = x[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < E; ++i) {
+                    uint32_t v = x[i];
+                    if (LAZY) v = ab_csub(v, 2 * q);
+                    if (LAZY) v = ab_csub(v, q);
+                    __stcs(yp + base + (i << S), (int64_t)v);
+                }
+            }
+        }
+    }
+}
+
+template <int LOGN, int LOGE, bool LAZY>
+__global__ void __launch_bounds__(Pow2Cfg<LOGN, LOGE>::THREADS, Pow2Cfg<LOGN, LOGE>::MINB)
+k_crt_pow2_inv(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
     using C = Pow2Cfg<LOGN, LOGE>;
     constexpr int E = C::E, T = C::T, G = C::G;
     extern __shared__ uint32_t smem[];
     const int tid = threadIdx.x, tl = tid & (T - 1), slot = tid / T;
-    int64_t trans = (int64_t)blockIdx.x * C::TPC + slot;
-    const bool active = trans < args.ntrans;
-    if (!active) trans = 0;
-    const Pow2Limb lp = args.limb[trans % args.nlimbs];
+    int64_t b = (int64_t)blockIdx.x * C::TPC + slot;
+    const bool active = b < args.batch;
+    if (!active) b = 0;
+    const Pow2Limb &lp = args.limb[blockIdx.y];
     const uint32_t q = lp.q;
     const uint2 *__restrict__ tw = lp.tw;
     uint32_t *sm = smem + slot * C::PADN;
-    int64_t *yp = y + trans * C::N;
+    int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * C::N;
 
     uint32_t x[E];
 #pragma unroll
     for (int w = C::NW - 1; w >= 0; --w) {
-        const int S = C::win_start(w), LB0 = C::win_lb0(w);
+        const int S = ab_pow2_s(LOGN, LOGE, w);
         const int low = tl & ((1 << S) - 1), high = tl >> S;
         const int base = low + (high << (S + LOGE));
         if (w == C::NW - 1) {
@@ -214,16 +320,11 @@ k_crt_pow2_inv(const Pow2Args args, int64_t *__restrict__ y) {
 #pragma unroll
             for (int i = 0; i < E; ++i) x[i] = active ? (uint32_t)__ldcs(yp + base + (i << S)) : 0u;
         } else {
-            if (C::win_start(w + 1) <= 5) __syncwarp(); else __syncthreads();
+            if (ab_pow2_s(LOGN, LOGE, w + 1) <= 5) __syncwarp(); else __syncthreads();
 #pragma unroll
             for (int i = 0; i < E; ++i) x[i] = sm[phys(base + (i << S))];
         }
-        switch (w) {
-            case 0: inv_window<LOGE, C::win_start(0), C::win_lb0(0), LAZY>(x, tw, low, q, lp.ninv, lp.ninv_s); break;
-            case 1: inv_window<LOGE, C::win_start(1), C::win_lb0(1), LAZY>(x, tw, low, q, lp.ninv, lp.ninv_s); break;
-            case 2: inv_window<LOGE, C::win_start(2), C::win_lb0(2), LAZY>(x, tw, low, q, lp.ninv, lp.ninv_s); break;
-            default: inv_window<LOGE, C::win_start(3), C::win_lb0(3), LAZY>(x, tw, low, q, lp.ninv, lp.ninv_s); break;
-        }
+        AB_RUN_INV_WINDOW(w)
 #pragma unroll
         for (int i = 0; i < E; ++i) sm[phys(base + (i << S))] = x[i];
     }
@@ -242,18 +343,39 @@ k_crt_pow2_inv(const Pow2Args args, int64_t *__restrict__ y) {
 }
 
 // ---------------------------------------------------------------------------------------------
+template <class K>
+static int resident_ctas(K kernel, int threads, size_t smem) {
+    int nb = 0;
+    AB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
+    return nb < 1 ? 1 : nb;
+}
+
 template <int LOGN, int LOGE, bool LAZY>
-static void launch_one(const Pow2Args &args, int64_t *y, bool inverse, cudaStream_t st) {
+static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool inverse, cudaStream_t st) {
     using C = Pow2Cfg<LOGN, LOGE>;
     const size_t smem = (size_t)C::TPC * C::PADN * sizeof(uint32_t);
-    const unsigned grid = (unsigned)((args.ntrans + C::TPC - 1) / C::TPC);
+    const dim3 grid((unsigned)((args.batch + C::TPC - 1) / C::TPC), (unsigned)args.nlimbs);
     if (inverse) {
         auto k = k_crt_pow2_inv<LOGN, LOGE, LAZY>;
-        if (smem > 48 * 1024) AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static thread_local bool ready = false;
+        if (!ready && smem > 48 * 1024) AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ready = true;
         k<<<grid, C::THREADS, smem, st>>>(args, y);
+    } else if constexpr (C::PIPE) {
+        auto k = k_crt_pow2_fwd_pipe<LOGN, LOGE, LAZY>;
+        static thread_local int per_sm = 0;
+        if (!per_sm) {
+            if (smem > 48 * 1024) AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            per_sm = resident_ctas(k, C::THREADS, smem);
+        }
+        // persistent: about one resident wave, split evenly over the limbs
+        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(args.batch, ((int64_t)p->sm_count * per_sm) / args.nlimbs));
+        k<<<dim3((unsigned)gx, (unsigned)args.nlimbs), C::THREADS, smem, st>>>(args, y);
     } else {
         auto k = k_crt_pow2_fwd<LOGN, LOGE, LAZY>;
-        if (smem > 48 * 1024) AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static thread_local bool ready = false;
+        if (!ready && smem > 48 * 1024) AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ready = true;
         k<<<grid, C::THREADS, smem, st>>>(args, y);
     }
     ab_count_launch();
@@ -261,21 +383,13 @@ static void launch_one(const Pow2Args &args, int64_t *y, bool inverse, cudaStrea
 }
 
 template <bool LAZY>
-static void dispatch_logn(int logn, const Pow2Args &args, int64_t *y, bool inverse, cudaStream_t st) {
-    switch (logn) {
-        case 5: launch_one<5, 5, LAZY>(args, y, inverse, st); break;
-        case 6: launch_one<6, 3, LAZY>(args, y, inverse, st); break;
-        case 7: launch_one<7, 4, LAZY>(args, y, inverse, st); break;
-        case 8: launch_one<8, 4, LAZY>(args, y, inverse, st); break;
-        case 9: launch_one<9, 5, LAZY>(args, y, inverse, st); break;
-        case 10: launch_one<10, 5, LAZY>(args, y, inverse, st); break;
-        case 11: launch_one<11, 5, LAZY>(args, y, inverse, st); break;
-        case 12: launch_one<12, 5, LAZY>(args, y, inverse, st); break;
-        case 13: launch_one<13, 5, LAZY>(args, y, inverse, st); break;
-        case 14: launch_one<14, 5, LAZY>(args, y, inverse, st); break;
-        case 15: launch_one<15, 5, LAZY>(args, y, inverse, st); break;
+static void dispatch_logn(const ab_plan *p, const Pow2Args &args, int64_t *y, bool inverse, cudaStream_t st) {
+#define AB_CASE(LN) case LN: launch_one<LN, ab_pow2_loge(LN), LAZY>(p, args, y, inverse, st); break;
+    switch (p->logn) {
+        AB_CASE(5) AB_CASE(6) AB_CASE(7) AB_CASE(8) AB_CASE(9) AB_CASE(10) AB_CASE(11) AB_CASE(12) AB_CASE(13) AB_CASE(14) AB_CASE(15)
         default: throw ab_error{AB_ERR_UNSUPPORTED, "pow2 kernel: unsupported size"};
     }
+#undef AB_CASE
 }
 
 bool ab_pow2_supported(const ab_plan *p) { return p->pow2 && p->has_crt && p->logn >= 5 && p->logn <= 15; }
@@ -287,7 +401,7 @@ void ab_launch_crt_pow2(const ab_plan *p, const AbView &v, bool inverse, cudaStr
     if (v.batch == 0) return;
     Pow2Args args{};
     args.nlimbs = v.nlimbs;
-    args.ntrans = v.batch * v.nlimbs;
+    args.batch = v.batch;
     bool lazy = true;
     for (int l = 0; l < v.nlimbs; ++l) {
         const AbLimbDev &ld = p->limb[v.limb0 + l];
@@ -295,8 +409,10 @@ void ab_launch_crt_pow2(const ab_plan *p, const AbView &v, bool inverse, cudaStr
         args.limb[l].ninv = ld.ninv;
         args.limb[l].ninv_s = ld.ninv_s;
         args.limb[l].tw = reinterpret_cast<const uint2 *>(inverse ? ld.tw_inv : ld.tw_fwd);
+        const uint2_ *t0 = inverse ? ld.tw0_inv : ld.tw0_fwd;
+        for (int k = 0; k < 32; ++k) args.limb[l].tw0[k] = make_uint2(t0[k].x, t0[k].y);
         if (ld.q >= (1u << 30)) lazy = false;
     }
-    if (lazy) dispatch_logn<true>(p->logn, args, v.y, inverse, st);
-    else dispatch_logn<false>(p->logn, args, v.y, inverse, st);
+    if (lazy) dispatch_logn<true>(p, args, v.y, inverse, st);
+    else dispatch_logn<false>(p, args, v.y, inverse, st);
 }

@@ -177,8 +177,31 @@ static void build_pow2_tables(ab_plan *pl, int limb, AbLimbDev &ld) {
             wi = mulmod(wi, ibase2, q);
         }
     }
-    ld.tw_fwd = dev_upload(pl, fwd);
-    ld.tw_inv = dev_upload(pl, inv);
+    // window-packed copies (ab_internal.h) for the kernel geometry chosen for this size
+    const int logn = pl->logn, loge = ab_pow2_loge(logn), nw = ab_pow2_nw(logn, loge);
+    if (logn >= 5 && logn <= 15) {
+        const int64_t total = ab_pow2_base(logn, loge, nw);
+        std::vector<uint2_> pf(total, uint2_{0, 0}), pi(total, uint2_{0, 0});
+        for (int w = 0; w < nw; ++w) {
+            const int S = ab_pow2_s(logn, loge, w), lb0 = ab_pow2_lb0(logn, loge, w), koff = ab_pow2_koff(logn, loge, w);
+            const int64_t base = ab_pow2_base(logn, loge, w);
+            for (int lb = lb0; lb < loge; ++lb)
+                for (int ip = 0; ip < (1 << lb); ++ip)
+                    for (int64_t low = 0; low < (1ll << S); ++low) {
+                        const int k = (1 << lb) + ip - koff;
+                        const int64_t src = (1ll << (S + lb)) + low + ((int64_t)ip << S);
+                        const int64_t dst = base + (((int64_t)(k >> 1) << S) + low) * 2 + (k & 1);
+                        pf[dst] = fwd[src];
+                        pi[dst] = inv[src];
+                    }
+        }
+        ld.tw_fwd = dev_upload(pl, pf);
+        ld.tw_inv = dev_upload(pl, pi);
+        for (int k = 0; k < 32; ++k) {
+            ld.tw0_fwd[k] = (k < (1 << loge) && (uint64_t)k < n) ? fwd[k] : uint2_{0, 0};
+            ld.tw0_inv[k] = (k < (1 << loge) && (uint64_t)k < n) ? inv[k] : uint2_{0, 0};
+        }
+    }
     ld.ninv = (uint32_t)ninv;
     ld.ninv_s = shoup(ninv, q);
 }
