@@ -28,6 +28,7 @@ void ab_crt_dispatch(const ab_plan *p, const AbView &v, bool inverse, cudaStream
     AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan was created without CRT tables");
     if (p->n == 1) return;   // m in {1, 2}: CRT is the identity
     if (ab_pow2_supported(p) && (v.layout == AB_LAYOUT_PLANAR || v.nlimbs == 1)) ab_launch_crt_pow2(p, v, inverse, st);
+    else if (ab_mixed_supported(p, v)) ab_launch_crt_mixed(p, v, inverse, st);
     else ab_launch_crt_generic(p, v, inverse, st);
 }
 void ab_crt_rows(const ab_plan *p, int64_t *y, int64_t rows, int32_t limb, bool inverse, cudaStream_t st) {

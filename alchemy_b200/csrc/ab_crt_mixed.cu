@@ -1,0 +1,319 @@
+// ab_crt_mixed.cu -- batched CRT / crtInv for arbitrary cyclotomic index m, prime moduli below 2^31 (sm_100a).
+//
+// Replaces lol-cpp `tensorCRTRq` / `tensorCRTInvRq` [RECALL] on the non-power-of-two rings of the reference's
+// examples (examples/Common.hs:41-54: m' = 11648 ... 54600) and of BASELINE config 3 (m = 40320).
+// One CTA owns one (ring element, limb): the n = phi(m) int64 residues are read once from HBM with 16-byte
+// loads and narrowed to uint32 in shared memory, the program of ab_mixed_plan.cpp runs out of shared memory,
+// and the result is written once: 16 n bytes of HBM traffic per transform, the algorithmic minimum.
+//
+// A dense step computes out_r = sum_c M[r][c] x_c for P <= 12 strided residues held in registers.  The
+// constants are stored as M * 2^32 mod q, the sum is accumulated exactly in 64 bits (IMAD.WIDE, one
+// instruction per term) and reduced ONCE per output with a Montgomery step: P + 4 instructions per output
+// instead of 7 per term.  The limb's constant tables (a few KB) sit in shared memory and are fetched with
+// 16-byte broadcast loads.  Radix-2 stages of the 2^e axis run three at a time on 8 residues per thread.
+#include <utility>
+
+#include "ab_internal.h"
+#include "ab_modarith.cuh"
+
+struct MxArgs {
+    AbMxStep steps[AB_MX_MAX_STEPS];
+    struct {
+        uint32_t q, qinv_neg;      // -q^-1 mod 2^32
+        const uint32_t *tab;
+        int32_t wide, pad;         // table layout of this limb (ab_mixed_plan.cpp)
+    } limb[AB_MAX_LIMBS];
+    int32_t nsteps, n, nlimbs;
+    int32_t tab_words[2];          // narrow, wide
+    int64_t batch;
+    int64_t estride, lstride, bstride;   // int64 strides of coefficient, limb, ring element
+};
+
+template <class F, int... I>
+__device__ __forceinline__ void mx_static_for_impl(F &&f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void mx_static_for(F &&f) {
+    mx_static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+// work item -> (tb, off): V adjacent columns per item, div_magic divides by estride / V
+template <int V>
+__device__ __forceinline__ void item_coords(const AbMxStep &s, int v, int &tb, int &off) {
+    const int es = s.estride / V;
+    tb = s.div_magic ? (int)__umulhi((uint32_t)v, s.div_magic) : v;
+    off = (v - tb * es) * V;
+}
+__device__ __forceinline__ int item_row(const AbMxStep &s, int tb, int off) {
+    if (s.row_mode == 1) return tb - (int)__umulhi((uint32_t)tb, s.row_magic) * s.rows;
+    if (s.row_mode == 2) return s.row_magic ? (int)__umulhi((uint32_t)off, s.row_magic) : off;
+    return 0;
+}
+template <int V>
+__device__ __forceinline__ void ld_cols(const uint32_t *p, uint32_t (&x)[V]) {
+    if (V == 2) { const uint2 t = *reinterpret_cast<const uint2 *>(p); x[0] = t.x; x[V - 1] = t.y; }
+    else x[0] = *p;
+}
+template <int V>
+__device__ __forceinline__ void st_cols(uint32_t *p, const uint32_t (&x)[V]) {
+    if (V == 2) *reinterpret_cast<uint2 *>(p) = make_uint2(x[0], x[V - 1]);
+    else *p = x[0];
+}
+
+// out = M x for V columns with one Montgomery reduction per output; x in [0,q), result in [0,q).
+// narrow (q < 2^30): T = sum x_c M'_c < P q^2, T + m q < 2^64, t < 4q.
+// WIDE  (q < 2^31): x = xh 2^16 + xl, T = sum xl_c M'_c + xh_c M''_c with M'' = M' 2^16: every term < 2^47.
+template <int P, int V, bool WIDE>
+__device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__restrict__ tab, const AbMxStep &s, int v, uint32_t q, uint32_t qinv_neg) {
+    constexpr int PP = (P + 3) & ~3, RW = WIDE ? 2 * PP : PP;
+    int tb, off;
+    item_coords<V>(s, v, tb, off);
+    const int es = s.estride;
+    uint32_t *e = sm + tb * (P * es) + off;
+    const uint4 *M = reinterpret_cast<const uint4 *>(tab + (WIDE ? s.tab_off_w : s.tab_off) + item_row(s, tb, off) * (P * RW));
+    uint32_t x[P][V];
+    mx_static_for<P>([&](auto C) { ld_cols<V>(e + decltype(C)::value * es, x[decltype(C)::value]); });
+    uint32_t xh[WIDE ? P : 1][V];
+    if (WIDE) {
+        mx_static_for<P>([&](auto C) {
+            constexpr int c = decltype(C)::value;
+#pragma unroll
+            for (int k = 0; k < V; ++k) { xh[WIDE ? c : 0][k] = x[c][k] >> 16; x[c][k] &= 0xffffu; }
+        });
+    }
+    mx_static_for<P>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        uint64_t acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0;
+        mx_static_for<PP / 4>([&](auto K) {
+            constexpr int k4 = decltype(K)::value;
+            const uint4 m4 = M[r * (RW / 4) + k4];
+            const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
+            mx_static_for<4>([&](auto J) {
+                constexpr int c = 4 * k4 + decltype(J)::value;
+                if (c < P) {
+#pragma unroll
+                    for (int k = 0; k < V; ++k) acc[k] += (uint64_t)x[c % P][k] * mm[decltype(J)::value];
+                }
+            });
+            if (WIDE) {
+                const uint4 h4 = M[r * (RW / 4) + PP / 4 + k4];
+                const uint32_t hh[4] = {h4.x, h4.y, h4.z, h4.w};
+                mx_static_for<4>([&](auto J) {
+                    constexpr int c = 4 * k4 + decltype(J)::value;
+                    if (c < P) {
+#pragma unroll
+                        for (int k = 0; k < V; ++k) acc[k] += (uint64_t)xh[WIDE ? c % P : 0][k] * hh[decltype(J)::value];
+                    }
+                });
+            }
+        });
+        uint32_t o[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const uint32_t mq = (uint32_t)acc[k] * qinv_neg;
+            uint32_t t = (uint32_t)((acc[k] + (uint64_t)mq * q) >> 32);
+            if (!WIDE && P > 4) t = ab_csub(t, 2 * q);
+            o[k] = ab_csub(t, q);
+        }
+        st_cols<V>(e + r * es, o);      // all inputs are already in registers: in place is safe
+    });
+}
+
+// G radix-2 stages on 2^G residues (V columns); forward: Cooley-Tukey (twiddle the upper input), inverse:
+// Gentleman-Sande.  LAZY (q < 2^30): Harvey butterflies, values in [0,4q) / [0,2q); otherwise exact.
+template <int G, int V, bool INV, bool LAZY>
+__device__ __forceinline__ void radix2_item(uint32_t *sm, const uint32_t *__restrict__ tab, const AbMxStep &s, int v, uint32_t q) {
+    constexpr int E = 1 << G;
+    int tb, off;
+    item_coords<V>(s, v, tb, off);
+    const int es = s.estride;
+    uint32_t *e = sm + tb * (E * es) + off;
+    const int l = item_row(s, tb, off);
+    const int h0 = s.rows;
+    const uint2 *T = reinterpret_cast<const uint2 *>(tab + (LAZY ? s.tab_off : s.tab_off_w));
+    uint32_t x[E][V];
+    mx_static_for<E>([&](auto C) { ld_cols<V>(e + decltype(C)::value * es, x[decltype(C)::value]); });
+    const bool last = INV && (s.flags & 1) != 0;
+    const uint2 sc = T[h0 * (E - 1)];
+    mx_static_for<G>([&](auto TT) {
+        constexpr int t = INV ? G - 1 - decltype(TT)::value : decltype(TT)::value;
+        const uint2 *Tt = T + h0 * ((1 << t) - 1) + l;
+        mx_static_for<(1 << t)>([&](auto LO) {
+            constexpr int lo = decltype(LO)::value;
+            const uint2 w = Tt[lo * h0];
+            mx_static_for<(E >> (t + 1))>([&](auto HI) {
+                constexpr int c = lo + (decltype(HI)::value << (t + 1)), d = c | (1 << t);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    if (!INV) {
+                        if (LAZY) {
+                            const uint32_t a = ab_csub(x[c][k], 2 * q);
+                            const uint32_t b = ab_shoup_lazy(x[d][k], w.x, w.y, q);
+                            x[c][k] = a + b;
+                            x[d][k] = a - b + 2 * q;
+                        } else {
+                            const uint32_t a = x[c][k], b = ab_shoup(x[d][k], w.x, w.y, q);
+                            x[c][k] = ab_addmod(a, b, q);
+                            x[d][k] = ab_submod(a, b, q);
+                        }
+                    } else {
+                        const uint32_t a = x[c][k], b = x[d][k];
+                        if (LAZY) {
+                            uint32_t sum = ab_csub(a + b, 2 * q);
+                            if (t == 0 && last) sum = ab_shoup_lazy(sum, sc.x, sc.y, q);
+                            x[c][k] = sum;
+                            x[d][k] = ab_shoup_lazy(a - b + 2 * q, w.x, w.y, q);
+                        } else {
+                            uint32_t sum = ab_addmod(a, b, q);
+                            if (t == 0 && last) sum = ab_shoup(sum, sc.x, sc.y, q);
+                            x[c][k] = sum;
+                            x[d][k] = ab_shoup(ab_submod(a, b, q), w.x, w.y, q);
+                        }
+                    }
+                }
+            });
+        });
+    });
+    mx_static_for<E>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        uint32_t o[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            uint32_t t = x[c][k];
+            if (LAZY && !INV) t = ab_csub(t, 2 * q);
+            if (LAZY) t = ab_csub(t, q);
+            o[k] = t;
+        }
+        st_cols<V>(e + c * es, o);
+    });
+}
+
+template <bool INV, bool WIDE>
+__device__ __forceinline__ void run_program(const MxArgs &args, uint32_t *sm, const uint32_t *tab, uint32_t q, uint32_t qinv_neg) {
+    for (int si = 0; si < args.nsteps; ++si) {
+        const AbMxStep &s = args.steps[si];
+        const int nw = s.nwork / s.vec;
+        if (s.kind == 0) {
+#define AB_MV(P)                                                                                                    \
+    case P:                                                                                                         \
+        if (s.vec == 2) for (int v = threadIdx.x; v < nw; v += blockDim.x) matvec_item<P, 2, WIDE>(sm, tab, s, v, q, qinv_neg); \
+        else for (int v = threadIdx.x; v < nw; v += blockDim.x) matvec_item<P, 1, WIDE>(sm, tab, s, v, q, qinv_neg);            \
+        break;
+            switch (s.span) {
+                AB_MV(2) AB_MV(3) AB_MV(4) AB_MV(5) AB_MV(6) AB_MV(7) AB_MV(10) AB_MV(11) AB_MV(12)
+                default: break;
+            }
+#undef AB_MV
+        } else {
+#define AB_R2(G)                                                                                                    \
+    case G:                                                                                                         \
+        if (s.vec == 2) for (int v = threadIdx.x; v < nw; v += blockDim.x) radix2_item<G, 2, INV, !WIDE>(sm, tab, s, v, q);     \
+        else for (int v = threadIdx.x; v < nw; v += blockDim.x) radix2_item<G, 1, INV, !WIDE>(sm, tab, s, v, q);                \
+        break;
+            switch (s.g) {
+                AB_R2(1) AB_R2(2)
+                default:
+                AB_R2(3)
+            }
+#undef AB_R2
+        }
+        __syncthreads();
+    }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(256, 4) k_crt_mixed(const __grid_constant__ MxArgs args, int64_t *__restrict__ y) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int limb = blockIdx.y;
+    const bool wide = args.limb[limb].wide != 0;
+    const int tab_words = args.tab_words[wide ? 1 : 0];
+    uint32_t *tab = smem;                          // [tab_words]
+    uint32_t *sm = smem + tab_words;               // [n]
+    const uint32_t q = args.limb[limb].q, qinv_neg = args.limb[limb].qinv_neg;
+    const int n = args.n;
+    int64_t *yp = y + blockIdx.x * args.bstride + limb * args.lstride;
+    {   // constant tables of this limb (L2-resident, a few KB)
+        const uint4 *src = reinterpret_cast<const uint4 *>(args.limb[limb].tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(tab);
+        for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (args.estride == 1) {
+        const int4 *src = reinterpret_cast<const int4 *>(yp);
+        uint2 *dst = reinterpret_cast<uint2 *>(sm);
+        for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+            const int4 v = __ldcs(src + i);
+            dst[i] = make_uint2((uint32_t)v.x, (uint32_t)v.z);
+        }
+    } else {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) sm[j] = (uint32_t)yp[j * args.estride];
+    }
+    __syncthreads();
+    if (wide) run_program<INV, true>(args, sm, tab, q, qinv_neg);
+    else run_program<INV, false>(args, sm, tab, q, qinv_neg);
+    if (args.estride == 1) {
+        int4 *dst = reinterpret_cast<int4 *>(yp);
+        const uint2 *src = reinterpret_cast<const uint2 *>(sm);
+        for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+            const uint2 v = src[i];
+            __stcs(dst + i, make_int4((int)v.x, 0, (int)v.y, 0));
+        }
+    } else {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) yp[j * args.estride] = (int64_t)sm[j];
+    }
+}
+
+bool ab_mixed_supported(const ab_plan *p, const AbView &v) {
+    if (p->mx_ok.empty() || p->mx_fwd.empty() || p->mx_tab_fwd.empty()) return false;
+    for (int l = 0; l < v.nlimbs; ++l)
+        if (!p->mx_ok[v.limb0 + l]) return false;
+    if (v.layout == AB_LAYOUT_PLANAR && (((uintptr_t)v.y & 15) != 0 || (p->n & 1))) return false;
+    return true;
+}
+
+static uint32_t neg_inv32(uint32_t q) {   // -q^-1 mod 2^32 (Newton)
+    uint32_t x = q;                        // q odd: x = q is an inverse mod 8
+    for (int i = 0; i < 5; ++i) x *= 2u - q * x;
+    return 0u - x;
+}
+
+void ab_launch_crt_mixed(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st) {
+    AB_REQUIRE(ab_mixed_supported(p, v), AB_ERR_UNSUPPORTED, "mixed kernel: plan not supported");
+    if (v.batch == 0) return;
+    MxArgs args{};
+    const auto &steps = inverse ? p->mx_inv : p->mx_fwd;
+    args.nsteps = (int32_t)steps.size();
+    for (size_t i = 0; i < steps.size(); ++i) args.steps[i] = steps[i];
+    args.n = (int32_t)p->n;
+    args.tab_words[0] = inverse ? p->mx_words_inv[0] : p->mx_words_fwd[0];
+    args.tab_words[1] = inverse ? p->mx_words_inv[1] : p->mx_words_fwd[1];
+    int max_words = 0;
+    args.nlimbs = v.nlimbs;
+    args.batch = v.batch;
+    if (v.layout == AB_LAYOUT_PLANAR) { args.estride = 1; args.lstride = p->n; args.bstride = p->n * v.nlimbs; }
+    else { args.estride = v.nlimbs; args.lstride = 1; args.bstride = p->n * v.nlimbs; }
+    for (int l = 0; l < v.nlimbs; ++l) {
+        const AbLimbDev &ld = p->limb[v.limb0 + l];
+        args.limb[l].q = ld.q;
+        args.limb[l].qinv_neg = neg_inv32(ld.q);
+        args.limb[l].tab = inverse ? p->mx_tab_inv[v.limb0 + l] : p->mx_tab_fwd[v.limb0 + l];
+        args.limb[l].wide = p->mx_ok[v.limb0 + l] == 2;
+        max_words = std::max(max_words, args.tab_words[args.limb[l].wide]);
+    }
+    const size_t smem = ((size_t)max_words + (size_t)p->n) * sizeof(uint32_t);
+    AB_REQUIRE(smem <= 227 * 1024, AB_ERR_UNSUPPORTED, "ring too large for the shared-memory transform");
+    static thread_local bool ready = false;
+    if (!ready) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_mixed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_mixed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ready = true;
+    }
+    // grid.x is limited to 2^31-1, grid.y = limbs
+    const dim3 grid((unsigned)v.batch, (unsigned)v.nlimbs);
+    if (inverse) k_crt_mixed<true><<<grid, 256, smem, st>>>(args, v.y);
+    else k_crt_mixed<false><<<grid, 256, smem, st>>>(args, v.y);
+    ab_count_launch();
+    ab_check_launch("crt_mixed");
+}

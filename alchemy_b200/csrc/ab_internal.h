@@ -127,6 +127,29 @@ struct AbGenStep {
     int32_t flags;      // kind 1 inverse: bit0 = multiply output 0 by table entry [h] (axis 2^-(e-1))
 };
 
+// ---------------------------------------------------------------------------------------------
+// fast mixed-radix program (ab_crt_mixed.cu): every step is one pass over the n residues of a transform held
+// in shared memory.  Work item v of a step: tb = v / estride, off = v % estride, base = tb*span*estride + off;
+// its `span` elements sit at base + k*estride.
+struct AbMxStep {
+    int32_t kind;        // 0 = dense span x span mat-vec (Montgomery constants), 1 = group of G radix-2 stages (Shoup twiddles)
+    int32_t span;        // mat-vec: P;  radix-2: 2^G
+    int32_t g;           // radix-2: G (1..3)
+    int32_t estride;
+    int32_t nwork;       // n / span
+    uint32_t div_magic;  // v / estride == umulhi(v, div_magic)           (0: estride == 1)
+    int32_t row_mode;    // matrix / twiddle row: 0 = none, 1 = tb % rows, 2 = off / sdiv
+    int32_t rows;
+    uint32_t row_magic;  // mode 1: tb / rows == umulhi(tb, row_magic); mode 2: off / sdiv == umulhi(off, row_magic)
+    int32_t sdiv;
+    int32_t tab_off;     // uint32 words into the limb's table block, narrow layout (q < 2^30)
+    int32_t tab_off_w;   // same for the wide layout (2^30 <= q < 2^31: two constants per matrix entry)
+    int32_t flags;       // radix-2 inverse: bit0 = this group ends the axis: fold 2^-(e-1) into the last stage
+    int32_t vec;         // 1 or 2 adjacent columns per work item (2: estride even, 8-byte shared-memory accesses);
+                         // div_magic then divides by estride / vec
+};
+#define AB_MX_MAX_STEPS 24
+
 struct AbAxis {
     int32_t p, e;
     int64_t pp, phi, mp;    // p^e, phi(p^e), p^(e-1)
@@ -147,6 +170,11 @@ struct ab_plan {
     std::vector<void *> owned;            // device allocations to free
     int device = 0;
     int sm_count = 148;
+    // fast mixed-radix program (moduli below 2^30 only; see ab_mixed_plan.cpp)
+    std::vector<AbMxStep> mx_fwd, mx_inv;
+    std::vector<const uint32_t *> mx_tab_fwd, mx_tab_inv;   // per limb, device
+    int32_t mx_words_fwd[2] = {0, 0}, mx_words_inv[2] = {0, 0};   // table block size (uint32 words): narrow, wide layout
+    std::vector<uint8_t> mx_ok;                             // per limb: 0 = not supported, 1 = narrow (q < 2^30), 2 = wide
     // host copies kept for tests / ext construction
     std::vector<int64_t> mhat_inv;        // per limb
 };
@@ -179,6 +207,9 @@ struct AbView {             // a batch of ring elements on the device
 void ab_launch_crt_pow2(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st);
 bool ab_pow2_supported(const ab_plan *p);
 void ab_launch_crt_generic(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st);
+void ab_build_mixed(ab_plan *pl);                                 // ab_mixed_plan.cpp
+bool ab_mixed_supported(const ab_plan *p, const AbView &v);       // ab_crt_mixed.cu
+void ab_launch_crt_mixed(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st);
 
 enum { AB_EW_MUL = 0, AB_EW_ADD = 1, AB_EW_SUB = 2, AB_EW_NEG = 3, AB_EW_SCALAR = 4, AB_EW_GCRT = 5, AB_EW_GINVCRT = 6 };
 void ab_launch_elementwise(const ab_plan *p, int op, const AbView &v, const int64_t *x, int64_t x_batch,

@@ -407,6 +407,7 @@ static void plan_build(ab_plan *pl, const ab_prime_exp *pe, int32_t npe, const i
     if (pl->pow2 && pl->n >= 2)
         for (int l = 0; l < L; ++l) build_pow2_tables(pl, l, pl->limb[l]);
     build_generic(pl);
+    ab_build_mixed(pl);
     // g at every CRT row
     std::vector<int64_t> units = crt_units(pl);
     for (int l = 0; l < L; ++l) {
