@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 
 #include "ab_internal.h"
@@ -190,24 +191,62 @@ struct DevBuf {
     DevBuf(const DevBuf &) = delete;
 };
 
+// Host-buffer calls are pipelined: the batch is cut into chunks of about 32 MB that rotate over three
+// internal streams (H2D copy, kernels, D2H copy of one chunk are stream-ordered; chunks on different streams
+// overlap), so the two PCIe directions and the kernels run concurrently.  With pinned host memory the copies
+// are truly asynchronous; with pageable memory the runtime stages them and the call still returns the same data.
+struct HostPipe {
+    static constexpr int kStreams = 3;
+    cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
+    int device = -1;
+    void ensure() {
+        int dev = 0;
+        AB_CHECK_CUDA(cudaGetDevice(&dev));
+        if (device == dev) return;
+        for (auto &s : st) {
+            if (s) cudaStreamDestroy(s);
+            AB_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        }
+        device = dev;
+    }
+};
+static thread_local HostPipe g_pipe;
+
 extern "C" int ab_tensor_op_host(const ab_plan *p, int op, int64_t *y_host, int64_t batch, int layout) {
     return ab_guard([&] {
         AB_REQUIRE(p && (y_host || batch == 0) && batch >= 0, AB_ERR_ARG, "bad arguments");
+        AB_REQUIRE(layout == AB_LAYOUT_PLANAR || layout == AB_LAYOUT_INTERLEAVED, AB_ERR_ARG, "unknown layout");
         if (batch == 0) return;
-        const size_t bytes = (size_t)batch * p->L * p->n * sizeof(int64_t);
-        cudaStream_t st = 0;
-        DevBuf d(bytes, st), t(layout == AB_LAYOUT_INTERLEAVED && p->L > 1 ? bytes : 0, st);
-        AB_CHECK_CUDA(cudaMemcpyAsync(d.p, y_host, bytes, cudaMemcpyHostToDevice, st));
-        if (layout == AB_LAYOUT_INTERLEAVED && p->L > 1) {
-            // de-interleave once on the device so every kernel streams contiguous limbs
-            ab_launch_layout(t.p, d.p, batch, p->L, p->n, true, st);
-            run_op(p, op, AbView{t.p, batch, 0, p->L, AB_LAYOUT_PLANAR}, st);
-            ab_launch_layout(d.p, t.p, batch, p->L, p->n, false, st);
-        } else {
-            run_op(p, op, AbView{d.p, batch, 0, p->L, AB_LAYOUT_PLANAR}, st);
+        g_pipe.ensure();
+        const size_t item = (size_t)p->L * p->n * sizeof(int64_t);
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)((32u << 20) / item)));
+        const bool relayout = layout == AB_LAYOUT_INTERLEAVED && p->L > 1;
+        const int ns = (int)std::min<int64_t>(HostPipe::kStreams, (batch + chunk - 1) / chunk);
+        std::vector<std::unique_ptr<DevBuf>> d(ns), t(ns);
+        for (int i = 0; i < ns; ++i) {
+            d[i].reset(new DevBuf(chunk * item, g_pipe.st[i]));
+            if (relayout) t[i].reset(new DevBuf(chunk * item, g_pipe.st[i]));
         }
-        AB_CHECK_CUDA(cudaMemcpyAsync(y_host, d.p, bytes, cudaMemcpyDeviceToHost, st));
-        AB_CHECK_CUDA(cudaStreamSynchronize(st));
+        int64_t k = 0;
+        for (int64_t b0 = 0; b0 < batch; b0 += chunk, ++k) {
+            const int i = (int)(k % ns);
+            cudaStream_t st = g_pipe.st[i];
+            const int64_t nb = std::min(chunk, batch - b0);
+            int64_t *h = y_host + b0 * (int64_t)(item / sizeof(int64_t));
+            AB_CHECK_CUDA(cudaMemcpyAsync(d[i]->p, h, nb * item, cudaMemcpyHostToDevice, st));
+            if (relayout) {
+                // de-interleave once on the device so every kernel streams contiguous limbs
+                ab_launch_layout(t[i]->p, d[i]->p, nb, p->L, p->n, true, st);
+                run_op(p, op, AbView{t[i]->p, nb, 0, p->L, AB_LAYOUT_PLANAR}, st);
+                ab_launch_layout(d[i]->p, t[i]->p, nb, p->L, p->n, false, st);
+            } else {
+                run_op(p, op, AbView{d[i]->p, nb, 0, p->L, AB_LAYOUT_PLANAR}, st);
+            }
+            AB_CHECK_CUDA(cudaMemcpyAsync(h, d[i]->p, nb * item, cudaMemcpyDeviceToHost, st));
+        }
+        d.clear();      // stream-ordered frees
+        t.clear();
+        for (int i = 0; i < ns; ++i) AB_CHECK_CUDA(cudaStreamSynchronize(g_pipe.st[i]));
     });
 }
 extern "C" int ab_mul_host(const ab_plan *p, int64_t *y_host, const int64_t *x_host, int64_t batch, int layout) {

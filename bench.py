@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="ring elements per GPU (default: ~1 GiB of residues)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-m2", action="store_true", help="skip the secondary mul+key-switch measurement")
     return ap.parse_args()
 
 
@@ -150,6 +151,38 @@ def run_reference(args):
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ M2
+def mul_keyswitch_leg(ab, torch, iters=5):
+    """PT2CT `mul_` pipeline modSwitch . keySwitchQuad . modSwitch . (*) (PT2CT.hs:172-177) on synthetic ciphertexts:
+    HomomRLWR's deepest level (m' = 20475, n = 8640, L 4 -> hint 5 -> 3, TrivGad) and Arithmetic.hs (m' = 512, 2 -> 2 -> 1)."""
+    from alchemy_b200 import she
+    out = []
+    for name, m, moduli, lin, lh, lout, B in (
+            ("HomomRLWR level 1", 20475, [1543651201, 689270401, 718099201, 720720001, 1556755201, 1567238401], 4, 5, 3, 256),
+            ("Arithmetic", 512, [268440577, 8392193, 1073750017], 2, 2, 1, 16384)):
+        plan = ab.Plan(m, moduli)
+        n = plan.n
+        rnd = lambda lead, L: torch.stack([torch.randint(0, q, tuple(lead) + (n,), dtype=torch.int64, device="cuda") for q in moduli[:L]], dim=-2)
+        a, b = rnd((B, 2), lin), rnd((B, 2), lin)
+        hint = rnd((lh, 2), lh)
+        lib = ab.lib()
+        for _ in range(2):
+            she.mulKeySwitch(plan, a, b, hint, lh, lout)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.ab_kernel_launches()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            she.mulKeySwitch(plan, a, b, hint, lh, lout)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        nbytes = (32 * n * lin + 16 * n * lout) * B
+        out.append({"workload": f"{name}: m'={m}, n={n}, L {lin}->{lh}->{lout}, B={B}", "ops_per_s": B / (ms * 1e-3), "ms": ms,
+                    "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "launches_per_call": int((lib.ab_kernel_launches() - l0) // iters)})
+    return out
 
 
 # ------------------------------------------------------------------------------------------ GPU legs
@@ -260,6 +293,11 @@ def main():
                "d2h_bytes_per_step": 2 * nbytes, "batch": eb, "steps": ksteps,
                "api": "ab_tensor_op_host(CRT) + ab_tensor_op_host(CRT_INV), pinned host buffers"}
 
+    # ---- secondary metric M2 (rank 0, N = 1 only): ciphertext mul + key-switch pipelines per second
+    m2 = None
+    if rank == 0 and world == 1 and not args.no_m2:
+        m2 = mul_keyswitch_leg(ab, torch)
+
     # ---- gather a checksum of every rank's result over NCCL (the only collective of the path)
     if world > 1:
         sums = [torch.zeros_like(ref_sum) for _ in range(world)]
@@ -282,6 +320,8 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks}
         if e2e:
             line["e2e"] = e2e
+        if m2:
+            line["mul_keyswitch"] = m2
         if not args.no_cpu:
             line["cpu_baseline"], _ = cpu_leg(m, n, moduli, target_s=10.0)
         print(json.dumps(line), flush=True)
