@@ -27,6 +27,7 @@ struct MxArgs {
     int32_t tab_words[2];          // narrow, wide
     int64_t batch;
     int64_t estride, lstride, bstride;   // int64 strides of coefficient, limb, ring element
+    AbMxFused fx;                        // fused load / store (ab_internal.h); all zero = plain in-place transform
 };
 
 template <class F, int... I>
@@ -240,7 +241,57 @@ __global__ void __launch_bounds__(256, 4) k_crt_mixed(const __grid_constant__ Mx
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
         for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    if (args.estride == 1) {
+    bool skip_program = false;
+    if (args.fx.load_mode == AB_MX_LOAD_DIGITS) {
+        // the residues of this transform are gadget digit d of a powerful-basis element (optionally gathered
+        // through an index table: coeffs . embed of the tunnel), centred and reduced into this CTA's modulus
+        const AbMxFused &fx = args.fx;
+        const int d = (int)(blockIdx.x % fx.nd);
+        const int64_t unit = blockIdx.x / fx.nd;
+        const uint32_t qs = fx.dig[d].q_src;
+        const int idx = fx.dig[d].idx, lastd = fx.dig[d].last, gb = fx.gbase;
+        if (gb == 0 && fx.triv_src != nullptr && fx.dig[d].limb == limb) {
+            // TrivGad digit of limb l reduced mod q_l is the element itself: its CRT is the caller's CRT-basis input
+            const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
+            int4 *dst = reinterpret_cast<int4 *>(yp);
+            for (int i = threadIdx.x; i < n / 2; i += blockDim.x) __stcs(dst + i, __ldcs(src + i));
+            return;
+        }
+        const int64_t su = fx.gK > 1 ? unit / fx.gK : unit;
+        const int32_t *gt = fx.gather ? fx.gather + (fx.gK > 1 ? (unit % fx.gK) * n : 0) : nullptr;
+        const int64_t *src = fx.src + su * fx.src_ustride + (int64_t)fx.dig[d].limb * fx.n_src;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            uint32_t v;
+            if (gt) { const int32_t g = __ldg(gt + j); v = g >= 0 ? (uint32_t)__ldg(src + g) : 0u; }
+            else v = (uint32_t)__ldcs(src + j);
+            int32_t c = ab_center(v, qs);
+            if (gb != 0) {
+                // Lol divModCent, `idx` times: floor division, remainder moved into [-b/2, b/2)
+                int32_t r = c;
+                for (int k = 0; k <= idx; ++k) {
+                    if (k == idx && lastd) { r = c; break; }
+                    int32_t qq = c / gb, rr = c - qq * gb;
+                    if (rr < 0) { rr += gb; qq -= 1; }
+                    if (2 * rr >= gb) { rr -= gb; qq += 1; }
+                    r = rr; c = qq;
+                }
+                c = r;
+            }
+            // reduce the signed digit into [0, q): |c| < 2q almost always (moduli of similar size)
+            uint32_t a = c < 0 ? (uint32_t)(-c) : (uint32_t)c;
+            if (a >= q) { a -= q; if (a >= q) a %= q; }
+            const uint32_t r = (c < 0 && a) ? q - a : a;
+            sm[j] = r;
+        }
+    } else if (args.fx.load_mode == AB_MX_LOAD_SRC) {
+        // out of place: read the transform from another planar buffer (e.g. c2 of a degree-2 ciphertext)
+        const int4 *src = reinterpret_cast<const int4 *>(args.fx.src + blockIdx.x * args.fx.src_ustride + (int64_t)(args.fx.src_limb0 + limb) * n);
+        uint2 *dst = reinterpret_cast<uint2 *>(sm);
+        for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+            const int4 v = __ldcs(src + i);
+            dst[i] = make_uint2((uint32_t)v.x, (uint32_t)v.z);
+        }
+    } else if (args.estride == 1) {
         const int4 *src = reinterpret_cast<const int4 *>(yp);
         uint2 *dst = reinterpret_cast<uint2 *>(sm);
         for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
@@ -250,10 +301,25 @@ __global__ void __launch_bounds__(256, 4) k_crt_mixed(const __grid_constant__ Mx
     } else {
         for (int j = threadIdx.x; j < n; j += blockDim.x) sm[j] = (uint32_t)yp[j * args.estride];
     }
+    (void)skip_program;
     __syncthreads();
     if (wide) run_program<INV, true>(args, sm, tab, q, qinv_neg);
     else run_program<INV, false>(args, sm, tab, q, qinv_neg);
-    if (args.estride == 1) {
+    if (args.fx.store_mode == AB_MX_STORE_SUBSCALE) {
+        // RNS rescale epilogue: out = (in - x) * q_drop^-1 mod q   (x = CRT of the lifted dropped limb)
+        const int64_t *in = args.fx.sub_in + blockIdx.x * args.fx.sub_ustride + (int64_t)limb * n;
+        const uint32_t sc = args.fx.scale[limb], scs = args.fx.scale_s[limb];
+        const int4 *src = reinterpret_cast<const int4 *>(in);
+        int4 *dst = reinterpret_cast<int4 *>(yp);
+        const uint2 *xs = reinterpret_cast<const uint2 *>(sm);
+        for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+            const int4 a = __ldcs(src + i);
+            const uint2 x = xs[i];
+            const uint32_t r0 = ab_shoup(ab_submod((uint32_t)a.x, x.x, q), sc, scs, q);
+            const uint32_t r1 = ab_shoup(ab_submod((uint32_t)a.z, x.y, q), sc, scs, q);
+            __stcs(dst + i, make_int4((int)r0, 0, (int)r1, 0));
+        }
+    } else if (args.estride == 1) {
         int4 *dst = reinterpret_cast<int4 *>(yp);
         const uint2 *src = reinterpret_cast<const uint2 *>(sm);
         for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
@@ -280,9 +346,16 @@ static uint32_t neg_inv32(uint32_t q) {   // -q^-1 mod 2^32 (Newton)
 }
 
 void ab_launch_crt_mixed(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st) {
+    ab_launch_crt_mixed_fused(p, v, inverse, nullptr, st);
+}
+
+// `v` describes the DESTINATION (planar): v.batch = number of transforms per limb (units * nd for digit loads)
+void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, const AbMxFused *fx, cudaStream_t st) {
     AB_REQUIRE(ab_mixed_supported(p, v), AB_ERR_UNSUPPORTED, "mixed kernel: plan not supported");
+    AB_REQUIRE(fx == nullptr || v.layout == AB_LAYOUT_PLANAR, AB_ERR_UNSUPPORTED, "fused modes need the planar layout");
     if (v.batch == 0) return;
     MxArgs args{};
+    if (fx) args.fx = *fx;
     const auto &steps = inverse ? p->mx_inv : p->mx_fwd;
     args.nsteps = (int32_t)steps.size();
     for (size_t i = 0; i < steps.size(); ++i) args.steps[i] = steps[i];

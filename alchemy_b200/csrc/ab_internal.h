@@ -150,6 +150,29 @@ struct AbMxStep {
 };
 #define AB_MX_MAX_STEPS 24
 
+// fused load / store of the mixed-radix CRT kernel (key switch, tunnel, modSwitch; ab_she.cpp)
+enum { AB_MX_LOAD_PLAIN = 0, AB_MX_LOAD_DIGITS = 1, AB_MX_LOAD_SRC = 2 };
+enum { AB_MX_STORE_PLAIN = 0, AB_MX_STORE_SUBSCALE = 1 };
+#define AB_MX_MAX_DIGITS 64
+struct AbMxFused {
+    int32_t load_mode, store_mode;
+    // AB_MX_LOAD_DIGITS: transform (unit * nd + d, limb l') = CRT of digit d of src[unit / gK] reduced mod q_l'
+    // AB_MX_LOAD_SRC:    transform (unit, limb) read from src + unit * src_ustride + (src_limb0 + limb) * n
+    int32_t nd, gbase;               // gbase 0 = TrivGad
+    const int64_t *src;              // powerful basis, planar [unit][limb][n_src]
+    int64_t src_ustride;
+    int32_t n_src, src_limb0;
+    const int32_t *gather;           // optional [gK][n]: index into the n_src source coefficients (-1 = zero)
+    int32_t gK, pad0;
+    const int64_t *triv_src;         // TrivGad: CRT-basis copy of the source (digit of limb l mod q_l needs no transform)
+    int64_t triv_ustride;
+    struct { uint32_t q_src; int16_t limb, idx; int16_t last, pad; } dig[AB_MX_MAX_DIGITS];
+    // AB_MX_STORE_SUBSCALE: y = (sub_in - x) * scale[limb]
+    const int64_t *sub_in;
+    int64_t sub_ustride;
+    uint32_t scale[AB_MAX_LIMBS], scale_s[AB_MAX_LIMBS];
+};
+
 struct AbAxis {
     int32_t p, e;
     int64_t pp, phi, mp;    // p^e, phi(p^e), p^(e-1)
@@ -210,6 +233,7 @@ void ab_launch_crt_generic(const ab_plan *p, const AbView &v, bool inverse, cuda
 void ab_build_mixed(ab_plan *pl);                                 // ab_mixed_plan.cpp
 bool ab_mixed_supported(const ab_plan *p, const AbView &v);       // ab_crt_mixed.cu
 void ab_launch_crt_mixed(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st);
+void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, const AbMxFused *fx, cudaStream_t st);
 
 enum { AB_EW_MUL = 0, AB_EW_ADD = 1, AB_EW_SUB = 2, AB_EW_NEG = 3, AB_EW_SCALAR = 4, AB_EW_GCRT = 5, AB_EW_GINVCRT = 6 };
 void ab_launch_elementwise(const ab_plan *p, int op, const AbView &v, const int64_t *x, int64_t x_batch,

@@ -11,12 +11,32 @@
 #include "ab_internal.h"
 #include "ab_kernels.h"
 
-static const int64_t kChunkBytes = 64ll << 20;   // scratch target per chunk: about half of the 126 MB L2
+static const int64_t kChunkBytes = 512ll << 20;   // scratch per chunk: large enough that every launch fills the 148 SMs
 
 static int64_t chunk_of(int64_t batch, int64_t bytes_per_item) {
     int64_t c = kChunkBytes / std::max<int64_t>(1, bytes_per_item);
     if (c < 1) c = 1;
     return std::min(batch, c);
+}
+
+// digit table of the product-ring gadget over the first `nlimbs` moduli (Lol: decompose (a,b) = decompose a ++ decompose b)
+static void fill_digits(const ab_plan *p, int32_t nlimbs, int32_t base, AbMxFused &fx, bool single_limb_src) {
+    int32_t nd = 0;
+    for (int l = 0; l < nlimbs; ++l) {
+        const int32_t k = ab_gadget_digits(p->q[l], base);
+        for (int i = 0; i < k; ++i, ++nd) {
+            AB_REQUIRE(nd < AB_MX_MAX_DIGITS, AB_ERR_UNSUPPORTED, "too many gadget digits");
+            fx.dig[nd].q_src = (uint32_t)p->q[l];
+            fx.dig[nd].limb = (int16_t)(single_limb_src ? 0 : l);
+            fx.dig[nd].idx = (int16_t)i;
+            fx.dig[nd].last = (int16_t)(i == k - 1);
+        }
+    }
+    fx.nd = nd;
+    fx.gbase = base;
+}
+static bool fused_ok(const ab_plan *p, int32_t nlimbs, const void *a, const void *b) {
+    return !ab_pow2_supported(p) && ab_mixed_supported(p, AbView{(int64_t *)a, 1, 0, nlimbs, AB_LAYOUT_PLANAR}) && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
 }
 
 extern "C" int ab_ct_mul_dev(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, void *stream) {
@@ -56,6 +76,27 @@ static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, i
         int64_t cur_stride = from * n;
         for (int32_t L = from; L > to; --L) {
             const int32_t d = L - 1;
+            if (fused_ok(p, L, cur, work) && ((uintptr_t)out & 15) == 0 && ((cur_stride * 8) % 16) == 0) {
+                // two launches per dropped limb: crtInv of that limb (out of place), then one kernel that lifts it,
+                // reduces it into each kept modulus, transforms it and applies (in - x) * q_d^-1 on the way out
+                AbMxFused fi{};
+                fi.load_mode = AB_MX_LOAD_SRC; fi.src = cur; fi.src_ustride = cur_stride; fi.src_limb0 = d;   // view limb0 = d selects the modulus
+                ab_launch_crt_mixed_fused(p, AbView{dropped, R, d, 1, AB_LAYOUT_PLANAR}, true, &fi, st);
+                AbMxFused fx{};
+                fx.load_mode = AB_MX_LOAD_DIGITS; fx.store_mode = AB_MX_STORE_SUBSCALE;
+                fx.nd = 1; fx.gbase = 0; fx.src = dropped; fx.src_ustride = n; fx.n_src = (int32_t)n; fx.gK = 1;
+                fx.dig[0].q_src = (uint32_t)p->q[d]; fx.dig[0].limb = 0; fx.dig[0].idx = 0; fx.dig[0].last = 1;
+                fx.sub_in = cur; fx.sub_ustride = cur_stride;
+                for (int k = 0; k < d; ++k) {
+                    const uint64_t inv = abh::invmod((uint64_t)p->q[d] % (uint64_t)p->q[k], (uint64_t)p->q[k]);
+                    fx.scale[k] = (uint32_t)inv; fx.scale_s[k] = abh::shoup(inv, (uint64_t)p->q[k]);
+                }
+                int64_t *dst_buf = (d == to) ? out + r0 * to * n : ((cur == ping) ? pong : ping);
+                ab_launch_crt_mixed_fused(p, AbView{dst_buf, R, 0, d, AB_LAYOUT_PLANAR}, false, &fx, st);
+                cur = dst_buf;
+                cur_stride = (int64_t)d * n;
+                continue;
+            }
             ab_launch_copy_rows(dropped, n, cur + (int64_t)d * n, cur_stride, n, R, st);
             ab_crt_rows(p, dropped, R, d, true, st);
             int32_t dst[AB_MAX_LIMBS];
@@ -107,6 +148,21 @@ extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int
             const int64_t B = std::min(chunk, batch - b0);
             int64_t *c2 = (int64_t *)work, *dig = c2 + B * per;
             const int64_t *in = in3 + b0 * 3 * per;
+            if (fused_ok(p, nlimbs, in, work)) {
+                // crtInv of c2 straight out of the input; then ONE launch that takes each gadget digit in the load
+                // phase of the forward CRT (TrivGad digits of limb l mod q_l are the CRT-basis input itself)
+                AbMxFused fi{};
+                fi.load_mode = AB_MX_LOAD_SRC; fi.src = in + 2 * per; fi.src_ustride = 3 * per; fi.src_limb0 = 0;
+                ab_launch_crt_mixed_fused(p, AbView{c2, B, 0, nlimbs, AB_LAYOUT_PLANAR}, true, &fi, st);
+                AbMxFused fx{};
+                fx.load_mode = AB_MX_LOAD_DIGITS;
+                fill_digits(p, nlimbs, base, fx, false);
+                fx.src = c2; fx.src_ustride = per; fx.n_src = (int32_t)n; fx.gK = 1;
+                if (base == 0) { fx.triv_src = in + 2 * per; fx.triv_ustride = 3 * per; }
+                ab_launch_crt_mixed_fused(p, AbView{dig, B * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, &fx, st);
+                ab_launch_hint_ip(p, out2 + b0 * 2 * per, 2 * per, dig, (int64_t)nd * per, hint, in, 3 * per, false, B, nlimbs, nd, st);
+                continue;
+            }
             // c2 -> powerful basis -> gadget digits reduced into every limb -> back to CRT
             ab_launch_copy_rows(c2, per, in + 2 * per, 3 * per, per, B, st);
             ab_crt_dispatch(p, AbView{c2, B, 0, nlimbs, AB_LAYOUT_PLANAR}, true, st);
@@ -224,9 +280,18 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
             // evalLin: c0' = sum_k p0_k * flin_k
             ab_launch_lin_ip(ps, lin, per_s, p0, K * per_s, flin, B, nlimbs, (int32_t)K, st);
             // c1: split over E' in the powerful basis (coeffsPow), embed (embedPow), decompose, reduce, CRT
-            ab_launch_tunnel_gather(ps, p1, cin + per_r, 2 * per_r, nr, t->d_pow, nullptr, B, K, nlimbs, st);
-            ab_launch_decompose(ps, dig, p1, B * K, nlimbs, nlimbs, base, st);
-            ab_crt_dispatch(ps, AbView{dig, B * K * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
+            if (fused_ok(ps, nlimbs, dig, cin)) {
+                // one launch: gather (coeffs . embed), gadget digit, reduction and forward CRT of O_s'
+                AbMxFused fx{};
+                fx.load_mode = AB_MX_LOAD_DIGITS;
+                fill_digits(ps, nlimbs, base, fx, false);
+                fx.src = cin + per_r; fx.src_ustride = 2 * per_r; fx.n_src = (int32_t)nr; fx.gather = t->d_pow; fx.gK = (int32_t)K;
+                ab_launch_crt_mixed_fused(ps, AbView{dig, B * K * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, &fx, st);
+            } else {
+                ab_launch_tunnel_gather(ps, p1, cin + per_r, 2 * per_r, nr, t->d_pow, nullptr, B, K, nlimbs, st);
+                ab_launch_decompose(ps, dig, p1, B * K, nlimbs, nlimbs, base, st);
+                ab_crt_dispatch(ps, AbView{dig, B * K * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
+            }
             // (c0'', c1'') = sum_{k,d} dig_{k,d} * hint_{k,d};  then c0'' += c0'
             ab_launch_hint_ip(ps, o, 2 * per_s, dig, K * nd * per_s, hint, nullptr, 0, false, B, nlimbs, (int32_t)(K * nd), st);
             ab_launch_add_rows(ps, o, 2 * per_s, lin, per_s, B, nlimbs, st);
