@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libalchemy_b200.so")
+LIB_PATH = os.environ.get("ALCHEMY_B200_LIB") or os.path.join(_HERE, "lib", "libalchemy_b200.so")   # env override: kernel-variant experiments
 
 AB_OK, AB_ERR_ARG, AB_ERR_NO_ROOT, AB_ERR_CUDA, AB_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 PLANAR, INTERLEAVED = 0, 1

@@ -30,6 +30,13 @@ struct MxArgs {
     AbMxFused fx;                        // fused load / store (ab_internal.h); all zero = plain in-place transform
 };
 
+#ifndef AB_MX_MINB
+#define AB_MX_MINB 4          // resident CTAs per SM the register budget is tuned for
+#endif
+#ifndef AB_MX_SPLIT
+#define AB_MX_SPLIT 0         // 1: two partial accumulators per output (shorter dependent chain); measured: no gain on B200
+#endif
+
 template <class F, int... I>
 __device__ __forceinline__ void mx_static_for_impl(F &&f, std::integer_sequence<int, I...>) {
     (f(std::integral_constant<int, I>{}), ...);
@@ -85,9 +92,9 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
     }
     mx_static_for<P>([&](auto R) {
         constexpr int r = decltype(R)::value;
-        uint64_t acc[V];
+        uint64_t acc[V], acc2[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] = 0;
+        for (int k = 0; k < V; ++k) acc[k] = acc2[k] = 0;
         mx_static_for<PP / 4>([&](auto K) {
             constexpr int k4 = decltype(K)::value;
             const uint4 m4 = M[r * (RW / 4) + k4];
@@ -96,7 +103,10 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
                 constexpr int c = 4 * k4 + decltype(J)::value;
                 if (c < P) {
 #pragma unroll
-                    for (int k = 0; k < V; ++k) acc[k] += (uint64_t)x[c % P][k] * mm[decltype(J)::value];
+                    for (int k = 0; k < V; ++k) {
+                        if (AB_MX_SPLIT && (c & 1)) acc2[k] += (uint64_t)x[c % P][k] * mm[decltype(J)::value];
+                        else acc[k] += (uint64_t)x[c % P][k] * mm[decltype(J)::value];
+                    }
                 }
             });
             if (WIDE) {
@@ -106,7 +116,10 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
                     constexpr int c = 4 * k4 + decltype(J)::value;
                     if (c < P) {
 #pragma unroll
-                        for (int k = 0; k < V; ++k) acc[k] += (uint64_t)xh[WIDE ? c % P : 0][k] * hh[decltype(J)::value];
+                        for (int k = 0; k < V; ++k) {
+                            if (AB_MX_SPLIT && (c & 1)) acc2[k] += (uint64_t)xh[WIDE ? c % P : 0][k] * hh[decltype(J)::value];
+                            else acc[k] += (uint64_t)xh[WIDE ? c % P : 0][k] * hh[decltype(J)::value];
+                        }
                     }
                 });
             }
@@ -114,6 +127,7 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
         uint32_t o[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
+            if (AB_MX_SPLIT) acc[k] += acc2[k];
             const uint32_t mq = (uint32_t)acc[k] * qinv_neg;
             uint32_t t = (uint32_t)((acc[k] + (uint64_t)mq * q) >> 32);
             if (!WIDE && P > 4) t = ab_csub(t, 2 * q);
@@ -226,7 +240,7 @@ __device__ __forceinline__ void run_program(const MxArgs &args, uint32_t *sm, co
 }
 
 template <bool INV>
-__global__ void __launch_bounds__(256, 4) k_crt_mixed(const __grid_constant__ MxArgs args, int64_t *__restrict__ y) {
+__global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_constant__ MxArgs args, int64_t *__restrict__ y) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int limb = blockIdx.y;
     const bool wide = args.limb[limb].wide != 0;
