@@ -263,7 +263,10 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
         const int d = (int)(blockIdx.x % fx.nd);
         const int64_t unit = blockIdx.x / fx.nd;
         const uint32_t qs = fx.dig[d].q_src;
-        const int idx = fx.dig[d].idx, lastd = fx.dig[d].last, gb = fx.gbase;
+        const int lastd = fx.dig[d].last, gb = fx.gbase, hb = fx.gbase / 2;
+        const uint32_t pw = fx.dig[d].pw;
+        const int64_t H = fx.dig[d].H;
+        const int pw_shift = (gb > 0 && (gb & (gb - 1)) == 0) ? 31 - __clz((int)pw) : -1;
         if (gb == 0 && fx.triv_src != nullptr && fx.dig[d].limb == limb) {
             // TrivGad digit of limb l reduced mod q_l is the element itself: its CRT is the caller's CRT-basis input
             const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
@@ -280,16 +283,19 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
             else v = (uint32_t)__ldcs(src + j);
             int32_t c = ab_center(v, qs);
             if (gb != 0) {
-                // Lol divModCent, `idx` times: floor division, remainder moved into [-b/2, b/2)
-                int32_t r = c;
-                for (int k = 0; k <= idx; ++k) {
-                    if (k == idx && lastd) { r = c; break; }
-                    int32_t qq = c / gb, rr = c - qq * gb;
-                    if (rr < 0) { rr += gb; qq -= 1; }
-                    if (2 * rr >= gb) { rr -= gb; qq += 1; }
-                    r = rr; c = qq;
+                // balanced base-b digit without iterating: ordinary digit of c + H, shifted (ab_internal.h)
+                const int64_t t = (int64_t)c + H;
+                int64_t qd;
+                if (pw_shift >= 0) qd = t >> pw_shift;                   // power-of-two base: arithmetic shift = floor
+                else if (t >= 0) qd = (int64_t)((uint32_t)t / pw);       // t < 2^32
+                else { qd = t / (int64_t)pw; if (qd * (int64_t)pw > t) qd -= 1; }
+                if (lastd) c = (int32_t)qd;
+                else {
+                    int32_t rr;
+                    if (pw_shift >= 0) rr = (int32_t)(qd & (gb - 1));
+                    else rr = (int32_t)(qd >= 0 ? (int64_t)((uint32_t)qd % (uint32_t)gb) : ((qd % gb) + gb) % gb);
+                    c = rr - hb;
                 }
-                c = r;
             }
             // reduce the signed digit into [0, q): |c| < 2q almost always (moduli of similar size)
             uint32_t a = c < 0 ? (uint32_t)(-c) : (uint32_t)c;

@@ -493,6 +493,108 @@ void ab_launch_hint_ip(const ab_plan *p, int64_t *out, int64_t out_bstride, cons
     ab_check_launch("hint_ip");
 }
 
+// Prepared hints: every hint residue h becomes the pair (h 2^32 mod q, h 2^48 mod q), so that the inner product
+// over the gadget digits can be accumulated exactly in 64 bits and reduced once (Montgomery) -- the same
+// arithmetic as the dense steps of ab_crt_mixed.cu.  rows = digits * 2; out[row][l][j] as uint2.
+struct HpArgs {
+    struct { uint32_t q, r32, r32_s, r16, r16_s, pad; } limb[AB_MAX_LIMBS];
+    int32_t nlimbs;
+    int64_t n, rows;
+};
+__global__ void __launch_bounds__(256) k_hint_prep(const HpArgs a, uint2 *__restrict__ out, const int64_t *__restrict__ hint) {
+    const int64_t per = (int64_t)a.nlimbs * a.n, total = a.rows * per;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)((i % per) / a.n);
+        const uint32_t q = a.limb[l].q;
+        const uint32_t h = (uint32_t)hint[i];
+        const uint32_t h32 = ab_shoup(h, a.limb[l].r32, a.limb[l].r32_s, q);
+        out[i] = make_uint2(h32, ab_shoup(h32, a.limb[l].r16, a.limb[l].r16_s, q));
+    }
+}
+void ab_launch_hint_prep(const ab_plan *p, void *out, const int64_t *hint, int64_t rows, int32_t nlimbs, cudaStream_t st) {
+    if (rows == 0) return;
+    HpArgs a{};
+    a.nlimbs = nlimbs; a.n = p->n; a.rows = rows;
+    for (int l = 0; l < nlimbs; ++l) {
+        const uint64_t q = p->q[l], r32 = (1ull << 32) % q, r16 = (1ull << 16) % q;
+        a.limb[l].q = (uint32_t)q; a.limb[l].r32 = (uint32_t)r32; a.limb[l].r32_s = abh::shoup(r32, q);
+        a.limb[l].r16 = (uint32_t)r16; a.limb[l].r16_s = abh::shoup(r16, q);
+    }
+    k_hint_prep<<<grid_for(rows * nlimbs * p->n, 256, p->sm_count), 256, 0, st>>>(a, reinterpret_cast<uint2 *>(out), hint);
+    ab_count_launch();
+    ab_check_launch("hint_prep");
+}
+
+// out[b][i][l][j] = add[b][i][l][j] + sum_d dig[b][d][l][j] * hint[d][i][l][j]   with prepared hints
+struct IpmArgs {
+    struct { uint32_t q, qinv_neg, wide, pad; uint64_t mu; } limb[AB_MAX_LIMBS];
+    int32_t nlimbs, ndig;
+    int64_t n, batch, dig_bstride, add_bstride, out_bstride;
+};
+template <bool WIDE>
+__device__ __forceinline__ void hint_ip_elem(const IpmArgs &a, int l, int64_t b, int64_t r, int64_t per, int64_t *__restrict__ out,
+                                             const int64_t *__restrict__ dig, const uint2 *__restrict__ hm, const int64_t *__restrict__ add) {
+    const uint32_t q = a.limb[l].q, qinv_neg = a.limb[l].qinv_neg;
+    uint64_t t0 = 0, t1 = 0;      // running 64-bit sums of full products
+    uint64_t s0 = 0, s1 = 0;      // sums of reduced chunks (narrow path)
+    const int64_t *dp = dig + b * a.dig_bstride + r;
+    const uint2 *hp = hm + r;
+    for (int d = 0; d < a.ndig; ++d) {
+        const uint32_t x = (uint32_t)__ldcs(dp + (int64_t)d * per);
+        const uint2 h0 = __ldg(hp + (int64_t)(2 * d) * per), h1 = __ldg(hp + (int64_t)(2 * d + 1) * per);
+        if (WIDE) {     // terms below 2^47: no intermediate reduction for any realistic digit count
+            const uint32_t xl = x & 0xffffu, xh = x >> 16;
+            t0 += (uint64_t)xl * h0.x + (uint64_t)xh * h0.y;
+            t1 += (uint64_t)xl * h1.x + (uint64_t)xh * h1.y;
+        } else {        // q < 2^30: products below 2^60, reduce every 8 terms
+            t0 += (uint64_t)x * h0.x;
+            t1 += (uint64_t)x * h1.x;
+            if ((d & 7) == 7) {
+                s0 += (t0 + (uint64_t)((uint32_t)t0 * qinv_neg) * q) >> 32; t0 = 0;
+                s1 += (t1 + (uint64_t)((uint32_t)t1 * qinv_neg) * q) >> 32; t1 = 0;
+            }
+        }
+    }
+    s0 += (t0 + (uint64_t)((uint32_t)t0 * qinv_neg) * q) >> 32;
+    s1 += (t1 + (uint64_t)((uint32_t)t1 * qinv_neg) * q) >> 32;
+    if (add) { s0 += (uint32_t)add[b * a.add_bstride + r]; s1 += (uint32_t)add[b * a.add_bstride + per + r]; }
+    // s < 2^32 * (ndig / 8 + 2): one Barrett reduction
+    const uint64_t mu = a.limb[l].mu;
+    uint64_t r0 = s0 - __umul64hi(s0, mu) * q, r1 = s1 - __umul64hi(s1, mu) * q;
+    if (r0 >= q) r0 -= q;
+    if (r1 >= q) r1 -= q;
+    out[b * a.out_bstride + r] = (int64_t)r0;
+    out[b * a.out_bstride + per + r] = (int64_t)r1;
+}
+__global__ void __launch_bounds__(256) k_hint_ip_m(const IpmArgs a, int64_t *__restrict__ out, const int64_t *__restrict__ dig,
+                                                   const uint2 *__restrict__ hm, const int64_t *__restrict__ add) {
+    const int64_t per = (int64_t)a.nlimbs * a.n, total = a.batch * per;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / per, r = i % per;
+        const int l = (int)(r / a.n);
+        if (a.limb[l].wide) hint_ip_elem<true>(a, l, b, r, per, out, dig, hm, add);
+        else hint_ip_elem<false>(a, l, b, r, per, out, dig, hm, add);
+    }
+}
+static uint32_t neg_inv32_ew(uint32_t q) {
+    uint32_t x = q;
+    for (int i = 0; i < 5; ++i) x *= 2u - q * x;
+    return 0u - x;
+}
+void ab_launch_hint_ip_m(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *dig, int64_t dig_bstride, const void *hm,
+                         const int64_t *add, int64_t add_bstride, int64_t batch, int32_t nlimbs, int32_t ndig, cudaStream_t st) {
+    if (batch == 0) return;
+    IpmArgs a{};
+    a.nlimbs = nlimbs; a.ndig = ndig; a.n = p->n; a.batch = batch; a.dig_bstride = dig_bstride; a.add_bstride = add_bstride; a.out_bstride = out_bstride;
+    for (int l = 0; l < nlimbs; ++l) {
+        a.limb[l].q = p->limb[l].q; a.limb[l].qinv_neg = neg_inv32_ew(p->limb[l].q); a.limb[l].mu = p->limb[l].mu;
+        a.limb[l].wide = p->limb[l].q >= (1u << 30);
+    }
+    k_hint_ip_m<<<grid_for(batch * nlimbs * p->n, 256, p->sm_count), 256, 0, st>>>(a, out, dig, reinterpret_cast<const uint2 *>(hm), add);
+    ab_count_launch();
+    ab_check_launch("hint_ip_m");
+}
+
 // acc[b][l][j] (+)= sum_k x[b][k][l][j] * f[k][l][j]      (evalLin of the tunnel's linear function)
 __global__ void __launch_bounds__(256) k_lin_ip(const IpArgs a, int64_t *__restrict__ out, const int64_t *__restrict__ x, const int64_t *__restrict__ f) {
     const int64_t per = (int64_t)a.nlimbs * a.n, total = a.batch * per;

@@ -166,7 +166,10 @@ struct AbMxFused {
     int32_t gK, pad0;
     const int64_t *triv_src;         // TrivGad: CRT-basis copy of the source (digit of limb l mod q_l needs no transform)
     int64_t triv_ustride;
-    struct { uint32_t q_src; int16_t limb, idx; int16_t last, pad; } dig[AB_MX_MAX_DIGITS];
+    // digit i of limb l (k digits, base b, hb = floor(b/2)): with H = hb (b^(k-1) - 1)/(b - 1), the balanced digits of
+    // Lol's iterated divModCent are the ordinary base-b digits of c + H shifted by hb:
+    //   d_i = (floor((c + H) / b^i) mod b) - hb  (i < k-1),   d_(k-1) = floor((c + H) / b^(k-1))
+    struct { uint32_t q_src, pw, H; int16_t limb, last; } dig[AB_MX_MAX_DIGITS];
     // AB_MX_STORE_SUBSCALE: y = (sub_in - x) * scale[limb]
     const int64_t *sub_in;
     int64_t sub_ustride;

@@ -16,6 +16,10 @@ void ab_launch_sub_scale(const ab_plan *p, int64_t *out, int64_t out_bstride, co
 void ab_launch_ct_mul(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, cudaStream_t st);
 void ab_launch_hint_ip(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *dig, int64_t dig_bstride, const int64_t *hint,
                        const int64_t *add, int64_t add_bstride, bool accumulate, int64_t batch, int32_t nlimbs, int32_t ndig, cudaStream_t st);
+// hints pre-multiplied by 2^32 / 2^48 (uint2 per residue), then the inner product with one reduction per output
+void ab_launch_hint_prep(const ab_plan *p, void *out, const int64_t *hint, int64_t rows, int32_t nlimbs, cudaStream_t st);
+void ab_launch_hint_ip_m(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *dig, int64_t dig_bstride, const void *hm,
+                         const int64_t *add, int64_t add_bstride, int64_t batch, int32_t nlimbs, int32_t ndig, cudaStream_t st);
 void ab_launch_lin_ip(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *x, int64_t x_bstride, const int64_t *f,
                       int64_t batch, int32_t nlimbs, int32_t nk, cudaStream_t st);
 void ab_launch_copy_rows(int64_t *out, int64_t ob, const int64_t *in, int64_t ib, int64_t len, int64_t batch, cudaStream_t st);

@@ -24,12 +24,18 @@ static void fill_digits(const ab_plan *p, int32_t nlimbs, int32_t base, AbMxFuse
     int32_t nd = 0;
     for (int l = 0; l < nlimbs; ++l) {
         const int32_t k = ab_gadget_digits(p->q[l], base);
+        uint64_t pw = 1, top = 1;                       // top = b^(k-1)
+        for (int i = 0; i + 1 < k; ++i) top *= (uint64_t)base;
+        const uint64_t H = base ? (uint64_t)(base / 2) * (top - 1) / (uint64_t)(base - 1) : 0;
         for (int i = 0; i < k; ++i, ++nd) {
             AB_REQUIRE(nd < AB_MX_MAX_DIGITS, AB_ERR_UNSUPPORTED, "too many gadget digits");
+            AB_REQUIRE(pw < (1ull << 32) && H < (1ull << 32), AB_ERR_UNSUPPORTED, "gadget base too large");
             fx.dig[nd].q_src = (uint32_t)p->q[l];
             fx.dig[nd].limb = (int16_t)(single_limb_src ? 0 : l);
-            fx.dig[nd].idx = (int16_t)i;
+            fx.dig[nd].pw = (uint32_t)pw;
+            fx.dig[nd].H = (uint32_t)H;
             fx.dig[nd].last = (int16_t)(i == k - 1);
+            pw *= (uint64_t)(base ? base : 1);
         }
     }
     fx.nd = nd;
@@ -85,7 +91,7 @@ static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, i
                 AbMxFused fx{};
                 fx.load_mode = AB_MX_LOAD_DIGITS; fx.store_mode = AB_MX_STORE_SUBSCALE;
                 fx.nd = 1; fx.gbase = 0; fx.src = dropped; fx.src_ustride = n; fx.n_src = (int32_t)n; fx.gK = 1;
-                fx.dig[0].q_src = (uint32_t)p->q[d]; fx.dig[0].limb = 0; fx.dig[0].idx = 0; fx.dig[0].last = 1;
+                fx.dig[0].q_src = (uint32_t)p->q[d]; fx.dig[0].limb = 0; fx.dig[0].pw = 1; fx.dig[0].H = 0; fx.dig[0].last = 1;
                 fx.sub_in = cur; fx.sub_ustride = cur_stride;
                 for (int k = 0; k < d; ++k) {
                     const uint64_t inv = abh::invmod((uint64_t)p->q[d] % (uint64_t)p->q[k], (uint64_t)p->q[k]);
@@ -132,7 +138,7 @@ extern "C" int64_t ab_key_switch_work_bytes(const ab_plan *p, int64_t batch, int
     const int32_t nd = ab_gadget_len(p, nlimbs, base);
     if (nd < 0 || batch < 0) return -1;
     const int64_t w = ks_item_words(p, nlimbs, nd);
-    return chunk_of(batch, w * 8) * w * 8;
+    return chunk_of(batch, w * 8) * w * 8 + (int64_t)nd * 2 * nlimbs * p->n * 8;     // + the prepared hint
 }
 extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int64_t *in3, const int64_t *hint, int64_t batch, int32_t nlimbs,
                                       int32_t base, void *work, void *stream) {
@@ -144,9 +150,12 @@ extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int
         cudaStream_t st = (cudaStream_t)stream;
         const int64_t n = p->n, per = (int64_t)nlimbs * n;
         const int64_t chunk = chunk_of(batch, ks_item_words(p, nlimbs, nd) * 8);
+        int64_t *hm = (int64_t *)work;                         // prepared hint: [nd][2][L][n] uint2
+        int64_t *work2 = hm + (int64_t)nd * 2 * per;
+        if (batch > 0) ab_launch_hint_prep(p, hm, hint, (int64_t)nd * 2, nlimbs, st);
         for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
             const int64_t B = std::min(chunk, batch - b0);
-            int64_t *c2 = (int64_t *)work, *dig = c2 + B * per;
+            int64_t *c2 = work2, *dig = c2 + B * per;
             const int64_t *in = in3 + b0 * 3 * per;
             if (fused_ok(p, nlimbs, in, work)) {
                 // crtInv of c2 straight out of the input; then ONE launch that takes each gadget digit in the load
@@ -160,7 +169,7 @@ extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int
                 fx.src = c2; fx.src_ustride = per; fx.n_src = (int32_t)n; fx.gK = 1;
                 if (base == 0) { fx.triv_src = in + 2 * per; fx.triv_ustride = 3 * per; }
                 ab_launch_crt_mixed_fused(p, AbView{dig, B * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, &fx, st);
-                ab_launch_hint_ip(p, out2 + b0 * 2 * per, 2 * per, dig, (int64_t)nd * per, hint, in, 3 * per, false, B, nlimbs, nd, st);
+                ab_launch_hint_ip_m(p, out2 + b0 * 2 * per, 2 * per, dig, (int64_t)nd * per, hm, in, 3 * per, B, nlimbs, nd, st);
                 continue;
             }
             // c2 -> powerful basis -> gadget digits reduced into every limb -> back to CRT
@@ -169,7 +178,7 @@ extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int
             ab_launch_decompose(p, dig, c2, B, nlimbs, nlimbs, base, st);
             ab_crt_dispatch(p, AbView{dig, B * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
             // (c0, c1) + sum_d dig_d * hint_d
-            ab_launch_hint_ip(p, out2 + b0 * 2 * per, 2 * per, dig, (int64_t)nd * per, hint, in, 3 * per, false, B, nlimbs, nd, st);
+            ab_launch_hint_ip_m(p, out2 + b0 * 2 * per, 2 * per, dig, (int64_t)nd * per, hm, in, 3 * per, B, nlimbs, nd, st);
         }
     });
 }
@@ -243,7 +252,7 @@ extern "C" int64_t ab_tunnel_work_bytes(const ab_tunnel *t, int64_t batch, int32
     const int32_t nd = ab_gadget_len(t->s, nlimbs, base);
     if (nd < 0) return -1;
     const int64_t w = tn_item_words(t, nlimbs, nd);
-    return chunk_of(batch, w * 8) * w * 8;
+    return chunk_of(batch, w * 8) * w * 8 + t->K * (int64_t)nd * 2 * nlimbs * t->s->n * 8;      // + the prepared hint
 }
 
 extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t *in2_r, const int64_t *flin, const int64_t *hint, int64_t batch,
@@ -259,9 +268,12 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
         const int64_t nr = pr->n, ns = ps->n, K = t->K;
         const int64_t per_r = (int64_t)nlimbs * nr, per_s = (int64_t)nlimbs * ns;
         const int64_t chunk = chunk_of(batch, tn_item_words(t, nlimbs, nd) * 8);
+        int64_t *hm = (int64_t *)work;               // prepared hint: [K][nd][2][L][n_s] uint2
+        int64_t *work2 = hm + K * (int64_t)nd * 2 * per_s;
+        if (batch > 0) ab_launch_hint_prep(ps, hm, hint, K * (int64_t)nd * 2, nlimbs, st);
         for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
             const int64_t B = std::min(chunk, batch - b0);
-            int64_t *cin = (int64_t *)work;          // [B][2][L][n_r]
+            int64_t *cin = work2;                    // [B][2][L][n_r]
             int64_t *c0d = cin + B * 2 * per_r;      // [B][L][n_r]
             int64_t *p0 = c0d + B * per_r;           // [B][K][L][n_s]
             int64_t *p1 = p0 + B * K * per_s;        // [B][K][L][n_s]
@@ -293,7 +305,7 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                 ab_crt_dispatch(ps, AbView{dig, B * K * nd, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
             }
             // (c0'', c1'') = sum_{k,d} dig_{k,d} * hint_{k,d};  then c0'' += c0'
-            ab_launch_hint_ip(ps, o, 2 * per_s, dig, K * nd * per_s, hint, nullptr, 0, false, B, nlimbs, (int32_t)(K * nd), st);
+            ab_launch_hint_ip_m(ps, o, 2 * per_s, dig, K * nd * per_s, hm, nullptr, 0, B, nlimbs, (int32_t)(K * nd), st);
             ab_launch_add_rows(ps, o, 2 * per_s, lin, per_s, B, nlimbs, st);
         }
     });

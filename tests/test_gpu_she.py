@@ -54,6 +54,10 @@ MULS = [  # (m, moduli, L_in, L_hint, L_out, base): the limb schedule of SURVEY.
     (20475, RLWR_Q, 1, 2, 1, 0),            # level 4
     (36, [37, 73, 109], 2, 3, 1, 0),
     (64, [193, 257, 449], 2, 2, 1, 4),      # BaseBGad on a product ring
+    (45, [181, 541, 631], 2, 3, 1, 3),      # odd base, mixed-radix ring (fused digit load)
+    (36, [37, 73, 109], 2, 2, 1, 2),        # binary gadget, mixed-radix ring
+    (11648, TUNNEL_Q, 2, 2, 1, 2),          # Tunnel.hs ring with its BaseBGad 2
+    (20475, RLWR_Q, 2, 2, 1, 16),
 ]
 
 
