@@ -60,6 +60,18 @@ def workload(args):
     return m, n, moduli, batch, name
 
 
+def measured_traffic(m, L, batch):
+    """DRAM bytes per launch of the two CRT kernels from the committed ncu capture (profiles/), if it is for this workload"""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    if t.get("workload_key") != f"m={m},L={L},B={batch}":
+        return None
+    return (t["k_crt_pow2_fwd_pipe"] + t["k_crt_pow2_inv"]) / 2
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -313,7 +325,7 @@ def main():
                 "data": "synthetic", "config": {"workload": name, "m": m, "n": n, "limbs": L, "batch_per_gpu": batch,
                                                  "l2": "in-place buffer of %.0f MB per GPU, larger than the 126 MB L2" % (batch * L * n * 8 / 1e6),
                                                  "step": "1 CRT launch + 1 crtInv launch over the whole batch"},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(m, L, batch),
                              "peak_source": peak_src, "kernel": "k_crt_pow2_fwd / k_crt_pow2_inv" if not args.m else "k_crt_generic",
                              "bytes_per_launch": bytes_per_launch, "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                              "fwd_gbs": bytes_per_launch / (fwd_ms * 1e-3) / 1e9, "inv_gbs": bytes_per_launch / (inv_ms * 1e-3) / 1e9},
