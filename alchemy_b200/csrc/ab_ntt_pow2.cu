@@ -22,6 +22,8 @@
 // algorithmic minimum.  Twiddles (Shoup pairs) are window-packed so one 16-byte load fetches two;
 // window 0's 31 twiddles are the same for every thread and travel as kernel constants.
 #include "ab_internal.h"
+#include <cooperative_groups.h>
+
 #include <utility>
 
 #include "ab_modarith.cuh"
@@ -63,6 +65,10 @@ __device__ __forceinline__ void bf_inv(uint32_t &X, uint32_t &Y, uint2 w, uint32
         Y = ab_shoup(d, w.x, w.y, q);
     }
 }
+
+#ifndef AB_POW2_CLUSTER
+#define AB_POW2_CLUSTER 1     // n = 32768: 2-CTA cluster kernels (0: single-CTA persistent / plain kernels)
+#endif
 
 template <int LOGN, int LOGE>
 struct Pow2Cfg {
@@ -343,6 +349,133 @@ k_crt_pow2_inv(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// n = 32768 as a 2-CTA cluster: each CTA (512 threads) owns half of the transform (16 blocks of 1024 residues,
+// 67.6 KB of shared memory), so TWO half-transforms of different clusters are resident per SM and their load,
+// butterfly and store phases overlap -- what a single 1024-thread CTA filling the SM cannot do.  Windows 0 and 1
+// stay inside 1024-residue blocks (warp-local); only the last window (stride 1024 ... 16384) crosses the halves:
+// its 32 inputs per thread come half from local and half from the peer CTA's shared memory (DSMEM).
+namespace cg = cooperative_groups;
+
+template <int LOGE, bool LAZY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 2)
+k_crt_pow2_fwd_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
+    constexpr int LOGN = 15, E = 1 << LOGE, G = 32;
+    static_assert(LOGE == 5, "cluster kernel: 3 windows of 5 stages");
+    extern __shared__ uint32_t sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned r = cluster.block_rank();
+    const int tl = threadIdx.x, wb = tl / G, lg = tl % G;
+    const int64_t b = blockIdx.x >> 1;
+    const Pow2Limb &lp = args.limb[blockIdx.y];
+    const uint32_t q = lp.q;
+    const uint2 *__restrict__ tw = lp.tw;
+    int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * (1 << LOGN);
+    {   // this warp's 1024-residue block of this CTA's half
+        const int4 *src = reinterpret_cast<const int4 *>(yp + (int64_t)(16 * r + wb) * G * E);
+#pragma unroll
+        for (int j0 = 0; j0 < E / 2; j0 += 8) {
+            int4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcs(src + lg + (j0 + j) * G);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int a = wb * G * E + 2 * (lg + (j0 + j) * G);
+                sm[phys(a)] = (uint32_t)v[j].x;
+                sm[phys(a + 1)] = (uint32_t)v[j].z;
+            }
+        }
+    }
+    __syncwarp();
+    uint32_t x[E];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {     // stages 0..9: inside the blocks of this half (local indices)
+        const int S = ab_pow2_s(LOGN, LOGE, w);
+        const int low = tl & ((1 << S) - 1), high = tl >> S;
+        const int base = low + (high << (S + LOGE));
+        if (w > 0) __syncwarp();
+#pragma unroll
+        for (int i = 0; i < E; ++i) x[i] = sm[phys(base + (i << S))];
+        AB_RUN_FWD_WINDOW(w)
+#pragma unroll
+        for (int i = 0; i < E; ++i) sm[phys(base + (i << S))] = x[i];
+    }
+    cluster.sync();      // both halves are complete (and both CTAs are running: first access to the peer's shared memory)
+    {
+        const int low = 512 * (int)r + tl;            // column of the last window, 0..1023
+        const uint32_t *peer = cluster.map_shared_rank(sm, r ^ 1);
+        const uint32_t *h0 = (r == 0) ? sm : peer, *h1 = (r == 0) ? peer : sm;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = h0[phys(i * 1024 + low)];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[16 + i] = h1[phys(i * 1024 + low)];
+        cluster.barrier_arrive();                     // my remote reads are done (waited for before exit)
+        AB_FW(2);
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            uint32_t v = x[i];
+            if (LAZY) v = ab_csub(v, 2 * q);
+            if (LAZY) v = ab_csub(v, q);
+            __stcs(yp + low + (i << 10), (int64_t)v);
+        }
+        cluster.barrier_wait();                       // the peer no longer reads my shared memory
+    }
+}
+
+template <int LOGE, bool LAZY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 2)
+k_crt_pow2_inv_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
+    constexpr int LOGN = 15, E = 1 << LOGE, G = 32;
+    extern __shared__ uint32_t sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned r = cluster.block_rank();
+    const int tl = threadIdx.x, wb = tl / G, lg = tl % G;
+    const int64_t b = blockIdx.x >> 1;
+    const Pow2Limb &lp = args.limb[blockIdx.y];
+    const uint32_t q = lp.q;
+    const uint2 *__restrict__ tw = lp.tw;
+    int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * (1 << LOGN);
+    uint32_t x[E];
+    cluster.barrier_arrive();   // "I am running": waited for just before the first store into the peer's shared memory
+    {   // stages 14..10 on this CTA's 512 columns, straight from HBM; results scattered to both halves
+        const int low = 512 * (int)r + tl;
+#pragma unroll
+        for (int i = 0; i < E; ++i) x[i] = (uint32_t)__ldcs(yp + low + (i << 10));
+        AB_IW(2);
+        cluster.barrier_wait();  // the peer is running
+        uint32_t *peer = cluster.map_shared_rank(sm, r ^ 1);
+        uint32_t *h0 = (r == 0) ? sm : peer, *h1 = (r == 0) ? peer : sm;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h0[phys(i * 1024 + low)] = x[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h1[phys(i * 1024 + low)] = x[16 + i];
+    }
+    cluster.sync();      // this half is complete (local and remote contributions)
+#pragma unroll
+    for (int w = 1; w >= 0; --w) {
+        const int S = ab_pow2_s(LOGN, LOGE, w);
+        const int low = tl & ((1 << S) - 1), high = tl >> S;
+        const int base = low + (high << (S + LOGE));
+        if (w < 1) __syncwarp();
+#pragma unroll
+        for (int i = 0; i < E; ++i) x[i] = sm[phys(base + (i << S))];
+        AB_RUN_INV_WINDOW(w)
+#pragma unroll
+        for (int i = 0; i < E; ++i) sm[phys(base + (i << S))] = x[i];
+    }
+    __syncwarp();
+    {
+        int4 *dst = reinterpret_cast<int4 *>(yp + (int64_t)(16 * r + wb) * G * E);
+#pragma unroll
+        for (int j = 0; j < E / 2; ++j) {
+            const int a = wb * G * E + 2 * (lg + j * G);
+            uint32_t v0 = sm[phys(a)], v1 = sm[phys(a + 1)];
+            if (LAZY) { v0 = ab_csub(v0, q); v1 = ab_csub(v1, q); }
+            __stcs(dst + lg + j * G, make_int4((int)v0, 0, (int)v1, 0));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <class K>
 static int resident_ctas(K kernel, int threads, size_t smem) {
     int nb = 0;
@@ -355,7 +488,18 @@ static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool 
     using C = Pow2Cfg<LOGN, LOGE>;
     const size_t smem = (size_t)C::TPC * C::PADN * sizeof(uint32_t);
     const dim3 grid((unsigned)((args.batch + C::TPC - 1) / C::TPC), (unsigned)args.nlimbs);
-    if (inverse) {
+    if constexpr (LOGN == 15 && AB_POW2_CLUSTER) {
+        constexpr size_t half = ((size_t)(1 << 14) + (1 << 9)) * sizeof(uint32_t);
+        static thread_local bool ready = false;
+        if (!ready) {
+            AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_fwd_c2<LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
+            AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_inv_c2<LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
+            ready = true;
+        }
+        const dim3 g2((unsigned)(2 * args.batch), (unsigned)args.nlimbs);
+        if (inverse) k_crt_pow2_inv_c2<LOGE, LAZY><<<g2, 512, half, st>>>(args, y);
+        else k_crt_pow2_fwd_c2<LOGE, LAZY><<<g2, 512, half, st>>>(args, y);
+    } else if (inverse) {
         auto k = k_crt_pow2_inv<LOGN, LOGE, LAZY>;
         static thread_local bool ready = false;
         if (!ready && smem > 48 * 1024) AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
