@@ -11,6 +11,9 @@
 // instruction per term) and reduced ONCE per output with a Montgomery step: P + 4 instructions per output
 // instead of 7 per term.  The limb's constant tables (a few KB) sit in shared memory and are fetched with
 // 16-byte broadcast loads.  Radix-2 stages of the 2^e axis run three at a time on 8 residues per thread.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
 #include <utility>
 
 #include "ab_internal.h"
@@ -239,6 +242,132 @@ __device__ __forceinline__ void run_program(const MxArgs &args, uint32_t *sm, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// gadget digit d of the powerful-basis element `su` (optionally gathered through row `krow` of an index table:
+// coeffs . embed of the tunnel), centred and reduced into the modulus q of this CTA -> sm[0..n)
+__device__ __forceinline__ bool mx_digit_is_trivial(const AbMxFused &fx, int d, int limb) {
+    return fx.gbase == 0 && fx.triv_src != nullptr && fx.dig[d].limb == limb;
+}
+__device__ __forceinline__ uint32_t mx_reduce_signed(int32_t c, uint32_t q) {
+    uint32_t a = c < 0 ? (uint32_t)(-c) : (uint32_t)c;
+    if (a >= q) { a -= q; if (a >= q) a %= q; }     // |c| < 2q almost always (moduli of similar size)
+    return (c < 0 && a) ? q - a : a;
+}
+__device__ __forceinline__ void mx_load_digit(const AbMxFused &fx, int d, int64_t su, int krow, int n, uint32_t q, uint32_t *sm) {
+    const uint32_t qs = fx.dig[d].q_src;
+    const int lastd = fx.dig[d].last, gb = fx.gbase, hb = fx.gbase / 2;
+    const uint32_t pw = fx.dig[d].pw;
+    const int64_t H = fx.dig[d].H;
+    const int pw_shift = (gb > 0 && (gb & (gb - 1)) == 0) ? 31 - __clz((int)pw) : -1;
+    const int32_t *__restrict__ gt = fx.gather ? fx.gather + (int64_t)krow * n : nullptr;
+    const int64_t *__restrict__ src = fx.src + su * fx.src_ustride + (int64_t)fx.dig[d].limb * fx.n_src;
+    const int T = blockDim.x;
+    for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {     // four loads in flight per thread
+        int32_t g[4];
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * T;
+            g[u] = j < n ? (gt ? __ldg(gt + j) : j) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = g[u] >= 0 ? (uint32_t)__ldg(src + g[u]) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * T;
+            if (j >= n) continue;
+            int32_t c = ab_center(v[u], qs);
+            if (gb != 0) {
+                // balanced base-b digit without iterating: ordinary digit of c + H, shifted (ab_internal.h)
+                const int64_t t = (int64_t)c + H;
+                int64_t qd;
+                if (pw_shift >= 0) qd = t >> pw_shift;                   // power-of-two base: arithmetic shift = floor
+                else if (t >= 0) qd = (int64_t)((uint32_t)t / pw);       // t < 2^32
+                else { qd = t / (int64_t)pw; if (qd * (int64_t)pw > t) qd -= 1; }
+                if (lastd) c = (int32_t)qd;
+                else if (pw_shift >= 0) c = (int32_t)(qd & (gb - 1)) - hb;
+                else c = (int32_t)(qd >= 0 ? (int64_t)((uint32_t)qd % (uint32_t)gb) : ((qd % gb) + gb) % gb) - hb;
+            }
+            sm[j] = mx_reduce_signed(c, q);
+        }
+    }
+}
+
+// Two-phase digit load for the fused inner product with a BaseBGad gadget, where the nd digits of one source limb
+// all come from the same centred coefficients: phase A gathers them ONCE per (k, source limb) -- the only place
+// with dependent loads (index table, then coefficient), issued four at a time -- and parks t = centred + H as
+// int64 in a scratch slice owned by this CTA; phase B cuts digit d out of t with shifts (power-of-two base) or
+// divisions and reduces it into this CTA's modulus.  Thread t touches the same positions in both phases.
+__device__ __forceinline__ void mx_gather_centered(const AbMxFused &fx, int d0, int64_t su, int krow, int n, int64_t *__restrict__ tbuf) {
+    const uint32_t qs = fx.dig[d0].q_src;
+    const int64_t H = fx.dig[d0].H;
+    const int32_t *__restrict__ gt = fx.gather ? fx.gather + (int64_t)krow * n : nullptr;
+    const int64_t *__restrict__ src = fx.src + su * fx.src_ustride + (int64_t)fx.dig[d0].limb * fx.n_src;
+    const int T = blockDim.x;
+    for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {
+        int32_t g[4];
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * T;
+            g[u] = j < n ? (gt ? __ldg(gt + j) : j) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = g[u] >= 0 ? (uint32_t)__ldg(src + g[u]) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * T;
+            if (j < n) __stcg(tbuf + j, (int64_t)ab_center(v[u], qs) + H);
+        }
+    }
+}
+__device__ __forceinline__ void mx_digit_from_t(const AbMxFused &fx, int d, int n, uint32_t q, const int64_t *__restrict__ tbuf, uint32_t *sm) {
+    const int lastd = fx.dig[d].last, gb = fx.gbase, hb = fx.gbase / 2;
+    const uint32_t pw = fx.dig[d].pw;
+    const int pw_shift = (gb > 0 && (gb & (gb - 1)) == 0) ? 31 - __clz((int)pw) : -1;
+    const int T = blockDim.x;
+    if (pw_shift >= 0 && !lastd && pw_shift + (31 - __clz(gb)) <= 32 && (uint32_t)hb < q) {
+        // power-of-two base, inner digit: the wanted bits of floor(t / 2^s) sit in the low word of t (two's complement),
+        // and |digit| <= b/2 < q needs no reduction
+        const uint32_t mask = (uint32_t)gb - 1u;
+        const uint32_t *lo = reinterpret_cast<const uint32_t *>(tbuf);
+        for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w[u] = (j0 + u * T < n) ? __ldcg(lo + 2 * (j0 + u * T)) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * T;
+                if (j < n) {
+                    const int32_t c = (int32_t)((w[u] >> pw_shift) & mask) - hb;
+                    sm[j] = c < 0 ? q + (uint32_t)c : (uint32_t)c;
+                }
+            }
+        }
+        return;
+    }
+    for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {
+        int64_t t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = (j0 + u * T < n) ? __ldcg(tbuf + j0 + u * T) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * T;
+            if (j < n) {
+                int64_t qd;
+                if (pw_shift >= 0) qd = t[u] >> pw_shift;                      // power-of-two base: arithmetic shift = floor
+                else if (t[u] >= 0) qd = (int64_t)((uint32_t)t[u] / pw);       // t < 2^32
+                else { qd = t[u] / (int64_t)pw; if (qd * (int64_t)pw > t[u]) qd -= 1; }
+                int32_t c;
+                if (lastd) c = (int32_t)qd;
+                else if (pw_shift >= 0) c = (int32_t)(qd & (gb - 1)) - hb;
+                else c = (int32_t)(qd >= 0 ? (int64_t)((uint32_t)qd % (uint32_t)gb) : ((qd % gb) + gb) % gb) - hb;
+                sm[j] = mx_reduce_signed(c, q);
+            }
+        }
+    }
+}
+
 template <bool INV>
 __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_constant__ MxArgs args, int64_t *__restrict__ y) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -262,47 +391,14 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
         const AbMxFused &fx = args.fx;
         const int d = (int)(blockIdx.x % fx.nd);
         const int64_t unit = blockIdx.x / fx.nd;
-        const uint32_t qs = fx.dig[d].q_src;
-        const int lastd = fx.dig[d].last, gb = fx.gbase, hb = fx.gbase / 2;
-        const uint32_t pw = fx.dig[d].pw;
-        const int64_t H = fx.dig[d].H;
-        const int pw_shift = (gb > 0 && (gb & (gb - 1)) == 0) ? 31 - __clz((int)pw) : -1;
-        if (gb == 0 && fx.triv_src != nullptr && fx.dig[d].limb == limb) {
+        if (mx_digit_is_trivial(fx, d, limb)) {
             // TrivGad digit of limb l reduced mod q_l is the element itself: its CRT is the caller's CRT-basis input
             const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
             int4 *dst = reinterpret_cast<int4 *>(yp);
             for (int i = threadIdx.x; i < n / 2; i += blockDim.x) __stcs(dst + i, __ldcs(src + i));
             return;
         }
-        const int64_t su = fx.gK > 1 ? unit / fx.gK : unit;
-        const int32_t *gt = fx.gather ? fx.gather + (fx.gK > 1 ? (unit % fx.gK) * n : 0) : nullptr;
-        const int64_t *src = fx.src + su * fx.src_ustride + (int64_t)fx.dig[d].limb * fx.n_src;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            uint32_t v;
-            if (gt) { const int32_t g = __ldg(gt + j); v = g >= 0 ? (uint32_t)__ldg(src + g) : 0u; }
-            else v = (uint32_t)__ldcs(src + j);
-            int32_t c = ab_center(v, qs);
-            if (gb != 0) {
-                // balanced base-b digit without iterating: ordinary digit of c + H, shifted (ab_internal.h)
-                const int64_t t = (int64_t)c + H;
-                int64_t qd;
-                if (pw_shift >= 0) qd = t >> pw_shift;                   // power-of-two base: arithmetic shift = floor
-                else if (t >= 0) qd = (int64_t)((uint32_t)t / pw);       // t < 2^32
-                else { qd = t / (int64_t)pw; if (qd * (int64_t)pw > t) qd -= 1; }
-                if (lastd) c = (int32_t)qd;
-                else {
-                    int32_t rr;
-                    if (pw_shift >= 0) rr = (int32_t)(qd & (gb - 1));
-                    else rr = (int32_t)(qd >= 0 ? (int64_t)((uint32_t)qd % (uint32_t)gb) : ((qd % gb) + gb) % gb);
-                    c = rr - hb;
-                }
-            }
-            // reduce the signed digit into [0, q): |c| < 2q almost always (moduli of similar size)
-            uint32_t a = c < 0 ? (uint32_t)(-c) : (uint32_t)c;
-            if (a >= q) { a -= q; if (a >= q) a %= q; }
-            const uint32_t r = (c < 0 && a) ? q - a : a;
-            sm[j] = r;
-        }
+        mx_load_digit(fx, d, fx.gK > 1 ? unit / fx.gK : unit, fx.gK > 1 ? (int)(unit % fx.gK) : 0, n, q, sm);
     } else if (args.fx.load_mode == AB_MX_LOAD_SRC) {
         // out of place: read the transform from another planar buffer (e.g. c2 of a degree-2 ciphertext)
         const int4 *src = reinterpret_cast<const int4 *>(args.fx.src + blockIdx.x * args.fx.src_ustride + (int64_t)(args.fx.src_limb0 + limb) * n);
@@ -351,12 +447,167 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused gadget inner product: out_c = add_c + sum_{k,d} CRT(reduce(digit_{k,d}(src))) * hint_{k,d,c},  c in {0,1}.
+// The core of keySwitchQuadCirc (Eval.hs:133) and of tunnel (Eval.hs:134).  One CTA owns (unit, limb) and keeps
+// the residues of the digit being transformed (uint32 [n]) and the two running sums (uint2 [n], fully reduced)
+// in shared memory for the whole loop: the K * nd digit transforms never touch HBM.  Per digit: load + centre +
+// digit + reduce (source and gather table from L2), the forward program, then one pass x * (h0, h1) with a
+// single-term Montgomery reduction each (T = x h 2^32 < 2^62, T + m q < 2^64 for q < 2^31).
+// ACC_SMEM = false: the running sums live in a global scratch slice owned by this CTA (thread t always touches the
+// same positions j = t, t + T, ..., so no synchronisation is needed; with one wave of CTAs resident the slices stay
+// in L2) and shared memory holds only the residues: the 4 x 256-thread residency of the plain transform is kept.
+template <int MAXT, int MINB, bool ACC_SMEM>
+__global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_constant__ MxArgs args, const __grid_constant__ AbMxMac mac) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int limb = blockIdx.y;
+    const bool wide = args.limb[limb].wide != 0;
+    const int tab_words = args.tab_words[wide ? 1 : 0];
+    const int n = args.n, nb = (n + 3) & ~3;
+    uint32_t *tab = smem;
+    uint32_t *sm = smem + tab_words;
+    const uint32_t q = args.limb[limb].q, qinv_neg = args.limb[limb].qinv_neg;
+    const AbMxFused &fx = args.fx;
+    const int64_t unit = blockIdx.x;
+    uint2 *acc = ACC_SMEM ? reinterpret_cast<uint2 *>(sm + nb)
+                          : reinterpret_cast<uint2 *>(mac.acc) + (unit * args.nlimbs + limb) * (int64_t)n;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(args.limb[limb].tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(tab);
+        for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    int64_t *tbuf = (mac.tbuf && fx.gbase != 0) ? mac.tbuf + (unit * args.nlimbs + limb) * (int64_t)n : nullptr;
+    const uint2 *hm = reinterpret_cast<const uint2 *>(mac.hm) + (int64_t)limb * n;
+    const int64_t hstride = (int64_t)args.nlimbs * n;
+    bool first = true;
+    for (int k = 0; k < mac.K; ++k) {
+        for (int d = 0; d < fx.nd; ++d) {
+            const bool triv = mx_digit_is_trivial(fx, d, limb);
+            if (triv) {
+                const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
+                uint2 *dst = reinterpret_cast<uint2 *>(sm);
+                for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+                    const int4 v = __ldcs(src + i);
+                    dst[i] = make_uint2((uint32_t)v.x, (uint32_t)v.z);
+                }
+            } else if (tbuf) {
+                if (d == 0 || fx.dig[d].limb != fx.dig[d - 1].limb) mx_gather_centered(fx, d, unit, k, n, tbuf);
+                mx_digit_from_t(fx, d, n, q, tbuf, sm);
+            } else {
+                mx_load_digit(fx, d, unit, k, n, q, sm);
+            }
+            __syncthreads();
+            if (!triv) {
+                if (wide) run_program<false, true>(args, sm, tab, q, qinv_neg);
+                else run_program<false, false>(args, sm, tab, q, qinv_neg);
+            }
+            const uint2 *hp = hm + (int64_t)(k * fx.nd + d) * hstride;
+            const int T = blockDim.x;
+            for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {
+                uint2 h[4], a[4];
+                uint32_t x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * T;
+                    const bool in = j < n;
+                    h[u] = in ? __ldg(hp + j) : make_uint2(0, 0);
+                    a[u] = (in && !first) ? (ACC_SMEM ? acc[j] : __ldcg(acc + j)) : make_uint2(0, 0);
+                    x[u] = in ? sm[j] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * T;
+                    if (j < n) {
+                        const uint64_t t0 = (uint64_t)x[u] * h[u].x, t1 = (uint64_t)x[u] * h[u].y;
+                        uint32_t r0 = (uint32_t)((t0 + (uint64_t)((uint32_t)t0 * qinv_neg) * q) >> 32);
+                        uint32_t r1 = (uint32_t)((t1 + (uint64_t)((uint32_t)t1 * qinv_neg) * q) >> 32);
+                        r0 = ab_addmod(ab_csub(r0, q), a[u].x, q);      // a = 0 on the first digit
+                        r1 = ab_addmod(ab_csub(r1, q), a[u].y, q);
+                        if (ACC_SMEM) acc[j] = make_uint2(r0, r1);
+                        else __stcg(acc + j, make_uint2(r0, r1));
+                    }
+                }
+            }
+            first = false;
+            __syncthreads();       // the next digit overwrites sm
+        }
+    }
+    {
+        const int64_t per = hstride;
+        int64_t *o0 = mac.out + unit * mac.out_ustride + (int64_t)limb * n, *o1 = o0 + per;
+        const int64_t *a0 = mac.add ? mac.add + unit * mac.add_ustride + (int64_t)limb * n : nullptr;
+        const int64_t *a1 = a0 ? a0 + per : nullptr;
+        const int64_t *l0 = mac.add0 ? mac.add0 + unit * mac.add0_ustride + (int64_t)limb * n : nullptr;
+        for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+            // positions 2i, 2i+1 were accumulated by other threads of this CTA: the barrier after the last digit orders them
+            const uint2 u = ACC_SMEM ? acc[2 * i] : __ldcg(acc + 2 * i), v = ACC_SMEM ? acc[2 * i + 1] : __ldcg(acc + 2 * i + 1);
+            uint32_t r00 = u.x, r01 = v.x, r10 = u.y, r11 = v.y;      // r[c][column]
+            if (a0) {
+                const int4 x0 = __ldcs(reinterpret_cast<const int4 *>(a0) + i), x1 = __ldcs(reinterpret_cast<const int4 *>(a1) + i);
+                r00 = ab_addmod(r00, (uint32_t)x0.x, q); r01 = ab_addmod(r01, (uint32_t)x0.z, q);
+                r10 = ab_addmod(r10, (uint32_t)x1.x, q); r11 = ab_addmod(r11, (uint32_t)x1.z, q);
+            }
+            if (l0) {
+                const int4 x0 = __ldcs(reinterpret_cast<const int4 *>(l0) + i);
+                r00 = ab_addmod(r00, (uint32_t)x0.x, q); r01 = ab_addmod(r01, (uint32_t)x0.z, q);
+            }
+            __stcs(reinterpret_cast<int4 *>(o0) + i, make_int4((int)r00, 0, (int)r01, 0));
+            __stcs(reinterpret_cast<int4 *>(o1) + i, make_int4((int)r10, 0, (int)r11, 0));
+        }
+    }
+}
+
 bool ab_mixed_supported(const ab_plan *p, const AbView &v) {
     if (p->mx_ok.empty() || p->mx_fwd.empty() || p->mx_tab_fwd.empty()) return false;
     for (int l = 0; l < v.nlimbs; ++l)
         if (!p->mx_ok[v.limb0 + l]) return false;
     if (v.layout == AB_LAYOUT_PLANAR && (((uintptr_t)v.y & 15) != 0 || (p->n & 1))) return false;
     return true;
+}
+
+// CTA size: every pass hands ceil(items / T) work items to each thread and ends in a barrier, so a T that does not
+// divide the item counts leaves threads idle in the last round (n = 9216, 12-point steps, two columns per item:
+// 384 items -> 1.5 rounds at T = 256).  Model: time of one transform ~ sum over passes of rounds * work per item,
+// throughput ~ resident CTAs / time; resident CTAs from shared memory and the 64-register budget (1024 threads).
+// Measured on B200 (tools/sweep_crt.py, AB_MX_T): within 3 % of the best of {128, 160, 192, 224, 256} on every example ring.
+// CTA size: every pass hands ceil(items / T) work items to each thread and ends in a barrier, so a T that does not
+// divide the item counts leaves threads idle in the last round (n = 9216, 12-point steps, two columns per item:
+// 384 items -> 1.5 rounds at T = 256).  Model: time of one transform ~ sum over passes of rounds * work per item,
+// throughput ~ resident CTAs / time; resident CTAs from shared memory and the 64-register budget (1024 threads).
+// Measured on B200 (tools/sweep_crt.py, AB_MX_T): within 3 % of the best of {128, 160, 192, 224, 256} on every example ring.
+// fixed number of resident CTAs (the caller's shared-memory budget decides it): the T that wastes the fewest thread
+// slots over the passes, larger T on ties
+static int pick_threads_among(const std::vector<AbMxStep> &steps, int n, std::initializer_list<int> cand) {
+    int best_t = *cand.begin();
+    double best = 1e300;
+    for (int T : cand) {
+        double time = 6.0 * ((n / 2 + T - 1) / T) + 20.0 * ((n + T - 1) / T);      // result store; digit load + multiply-accumulate
+        for (const AbMxStep &s : steps) {
+            const int items = s.nwork / s.vec, rounds = (items + T - 1) / T;
+            const double w = s.kind == 0 ? (double)s.span * s.vec * (s.span + 6) : (double)s.span * s.vec * (3.5 * s.g + 2);
+            time += rounds * w;
+        }
+        // idle threads still hold registers: prefer the T with the least time, then the smaller footprint
+        if (time < best * 0.9999 || (time < best * 1.0001 && T > best_t)) { best = time; best_t = T; }
+    }
+    return best_t;
+}
+static int pick_threads(const std::vector<AbMxStep> &steps, int n, size_t smem) {
+    int best_t = 256;
+    double best = 0;
+    for (int T : {128, 160, 192, 256}) {
+        const int ctas = (int)std::min<size_t>((size_t)(1024 / T), (size_t)(227 * 1024) / (smem + 1024));
+        if (ctas < 1) continue;
+        double time = 6.0 * ((n / 2 + T - 1) / T);                 // load + store phases
+        for (const AbMxStep &s : steps) {
+            const int items = s.nwork / s.vec, rounds = (items + T - 1) / T;
+            const double w = s.kind == 0 ? (double)s.span * s.vec * (s.span + 6) : (double)s.span * s.vec * (3.5 * s.g + 2);
+            time += rounds * w;
+        }
+        const double tput = ctas / time;
+        if (tput > best * 1.0001) { best = tput; best_t = T; }
+    }
+    return best_t;
 }
 
 static uint32_t neg_inv32(uint32_t q) {   // -q^-1 mod 2^32 (Newton)
@@ -405,8 +656,76 @@ void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, 
     }
     // grid.x is limited to 2^31-1, grid.y = limbs
     const dim3 grid((unsigned)v.batch, (unsigned)v.nlimbs);
-    if (inverse) k_crt_mixed<true><<<grid, 256, smem, st>>>(args, v.y);
-    else k_crt_mixed<false><<<grid, 256, smem, st>>>(args, v.y);
+    static const int force_t = getenv("AB_MX_T") ? atoi(getenv("AB_MX_T")) : 0;      // experiments only
+    const int T = force_t ? force_t : pick_threads(steps, (int)p->n, smem);
+    if (inverse) k_crt_mixed<true><<<grid, T, smem, st>>>(args, v.y);
+    else k_crt_mixed<false><<<grid, T, smem, st>>>(args, v.y);
     ab_count_launch();
     ab_check_launch("crt_mixed");
+}
+
+static void fill_mx_args(const ab_plan *p, MxArgs &args, int32_t limb0, int32_t nlimbs, bool inverse, int &max_words) {
+    const auto &steps = inverse ? p->mx_inv : p->mx_fwd;
+    args.nsteps = (int32_t)steps.size();
+    for (size_t i = 0; i < steps.size(); ++i) args.steps[i] = steps[i];
+    args.n = (int32_t)p->n;
+    args.tab_words[0] = inverse ? p->mx_words_inv[0] : p->mx_words_fwd[0];
+    args.tab_words[1] = inverse ? p->mx_words_inv[1] : p->mx_words_fwd[1];
+    args.nlimbs = nlimbs;
+    max_words = 0;
+    for (int l = 0; l < nlimbs; ++l) {
+        const AbLimbDev &ld = p->limb[limb0 + l];
+        args.limb[l].q = ld.q;
+        args.limb[l].qinv_neg = neg_inv32(ld.q);
+        args.limb[l].tab = inverse ? p->mx_tab_inv[limb0 + l] : p->mx_tab_fwd[limb0 + l];
+        args.limb[l].wide = p->mx_ok[limb0 + l] == 2;
+        max_words = std::max(max_words, args.tab_words[args.limb[l].wide]);
+    }
+}
+
+static size_t mac_smem(const ab_plan *p, int max_words, bool acc_smem) {
+    const size_t nb = ((size_t)p->n + 3) & ~(size_t)3;
+    return ((size_t)max_words + nb + (acc_smem ? 2 * (size_t)p->n : 0)) * sizeof(uint32_t);
+}
+// the running sums ride in shared memory only where four CTAs still fit an SM; otherwise in the caller's scratch
+static bool mac_acc_in_smem(const ab_plan *p, int max_words) { return 4 * (mac_smem(p, max_words, true) + 1024) <= 228 * 1024; }
+bool ab_mixed_mac_supported(const ab_plan *p, int32_t nlimbs) {
+    if (ab_pow2_supported(p) || (p->n & 1)) return false;
+    return ab_mixed_supported(p, AbView{nullptr, 1, 0, nlimbs, AB_LAYOUT_INTERLEAVED});
+}
+int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs) {
+    const int words = std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]);
+    return mac_acc_in_smem(p, words) ? 0 : units * nlimbs * p->n;      // uint2 per position = one int64 word
+}
+
+template <bool ACC_SMEM>
+static void launch_mac(const MxArgs &args, const AbMxMac &mac, dim3 grid, int T, size_t smem, cudaStream_t st) {
+    static thread_local bool ready = false;
+    if (!ready) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_mixed_mac<256, AB_MX_MINB, ACC_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ready = true;
+    }
+    k_crt_mixed_mac<256, AB_MX_MINB, ACC_SMEM><<<grid, T, smem, st>>>(args, mac);
+}
+
+void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, const AbMxFused &fx, const AbMxMac &mac, cudaStream_t st) {
+    AB_REQUIRE(ab_mixed_mac_supported(p, nlimbs), AB_ERR_UNSUPPORTED, "fused gadget inner product: plan not supported");
+    AB_REQUIRE(fx.load_mode == AB_MX_LOAD_DIGITS && fx.nd >= 1 && mac.K >= 1 && mac.hm && mac.out, AB_ERR_ARG, "fused gadget inner product: bad arguments");
+    if (units == 0) return;
+    MxArgs args{};
+    args.fx = fx;
+    int max_words = 0;
+    fill_mx_args(p, args, 0, nlimbs, false, max_words);
+    args.batch = units;
+    args.estride = 1; args.lstride = p->n; args.bstride = p->n * nlimbs;
+    const bool acc_smem = mac_acc_in_smem(p, std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]));
+    AB_REQUIRE(acc_smem || mac.acc, AB_ERR_ARG, "fused gadget inner product: scratch missing");
+    const size_t smem = mac_smem(p, max_words, acc_smem);
+    static const int force_t = getenv("AB_MX_MAC_T") ? atoi(getenv("AB_MX_MAC_T")) : 0;      // experiments only
+    const int T = force_t ? force_t : pick_threads(p->mx_fwd, (int)p->n, smem);
+    const dim3 grid((unsigned)units, (unsigned)nlimbs);
+    if (acc_smem) launch_mac<true>(args, mac, grid, T, smem, st);
+    else launch_mac<false>(args, mac, grid, T, smem, st);
+    ab_count_launch();
+    ab_check_launch("crt_mixed_mac");
 }

@@ -525,6 +525,31 @@ void ab_launch_hint_prep(const ab_plan *p, void *out, const int64_t *hint, int64
     ab_check_launch("hint_prep");
 }
 
+// Prepared hints of the fused gadget inner product (k_crt_mixed_mac): both components of a digit's hint side by
+// side, each pre-multiplied by 2^32:  out[kd][l][j] = (hint[kd][0][l][j] 2^32 mod q_l, hint[kd][1][l][j] 2^32 mod q_l)
+__global__ void __launch_bounds__(256) k_hint_prep2(const HpArgs a, uint2 *__restrict__ out, const int64_t *__restrict__ hint) {
+    const int64_t per = (int64_t)a.nlimbs * a.n, total = a.rows * per;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t kd = i / per, r = i % per;
+        const int l = (int)(r / a.n);
+        const uint32_t q = a.limb[l].q;
+        const uint32_t h0 = (uint32_t)hint[(2 * kd) * per + r], h1 = (uint32_t)hint[(2 * kd + 1) * per + r];
+        out[i] = make_uint2(ab_shoup(h0, a.limb[l].r32, a.limb[l].r32_s, q), ab_shoup(h1, a.limb[l].r32, a.limb[l].r32_s, q));
+    }
+}
+void ab_launch_hint_prep2(const ab_plan *p, void *out, const int64_t *hint, int64_t ndig, int32_t nlimbs, cudaStream_t st) {
+    if (ndig == 0) return;
+    HpArgs a{};
+    a.nlimbs = nlimbs; a.n = p->n; a.rows = ndig;
+    for (int l = 0; l < nlimbs; ++l) {
+        const uint64_t q = p->q[l], r32 = (1ull << 32) % q;
+        a.limb[l].q = (uint32_t)q; a.limb[l].r32 = (uint32_t)r32; a.limb[l].r32_s = abh::shoup(r32, q);
+    }
+    k_hint_prep2<<<grid_for(ndig * nlimbs * p->n, 256, p->sm_count), 256, 0, st>>>(a, reinterpret_cast<uint2 *>(out), hint);
+    ab_count_launch();
+    ab_check_launch("hint_prep2");
+}
+
 // out[b][i][l][j] = add[b][i][l][j] + sum_d dig[b][d][l][j] * hint[d][i][l][j]   with prepared hints
 struct IpmArgs {
     struct { uint32_t q, qinv_neg, wide, pad; uint64_t mu; } limb[AB_MAX_LIMBS];

@@ -176,6 +176,22 @@ struct AbMxFused {
     uint32_t scale[AB_MAX_LIMBS], scale_s[AB_MAX_LIMBS];
 };
 
+// fused gadget inner product (ab_crt_mixed.cu, k_crt_mixed_mac): one CTA per (unit, limb) walks over the K * nd
+// gadget digits of the unit -- digit extraction, forward CRT and the multiply-accumulate against the prepared
+// hint all happen in shared memory; only the two result polynomials leave the SM.
+struct AbMxMac {
+    const void *hm;              // prepared hint [K * nd][L][n] of uint2 = (h_0 2^32 mod q, h_1 2^32 mod q)  (ab_launch_hint_prep2)
+    int32_t K, pad;              // tunnel: dimension of O_r' over O_e' (digit loop runs over K * nd); key switch: 1
+    const int64_t *add;          // optional [unit][2][L][n] added to both components (key switch: c0, c1)
+    int64_t add_ustride;
+    const int64_t *add0;         // optional [unit][L][n] added to component 0 (tunnel: the evalLin part)
+    int64_t add0_ustride;
+    void *acc;                   // scratch of ab_mixed_mac_scratch_words() int64 words (may be null when that is 0)
+    int64_t *tbuf;               // optional scratch [unit][L][n] int64: centred source + H, gathered once per (k, source limb)
+    int64_t *out;                // [unit][2][L][n]
+    int64_t out_ustride;
+};
+
 struct AbAxis {
     int32_t p, e;
     int64_t pp, phi, mp;    // p^e, phi(p^e), p^(e-1)
@@ -237,6 +253,10 @@ void ab_build_mixed(ab_plan *pl);                                 // ab_mixed_pl
 bool ab_mixed_supported(const ab_plan *p, const AbView &v);       // ab_crt_mixed.cu
 void ab_launch_crt_mixed(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st);
 void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, const AbMxFused *fx, cudaStream_t st);
+// units x nlimbs CTAs; fx describes the digit source (load_mode AB_MX_LOAD_DIGITS); plan p = the ring the digits live in
+bool ab_mixed_mac_supported(const ab_plan *p, int32_t nlimbs);
+int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs);
+void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, const AbMxFused &fx, const AbMxMac &mac, cudaStream_t st);
 
 enum { AB_EW_MUL = 0, AB_EW_ADD = 1, AB_EW_SUB = 2, AB_EW_NEG = 3, AB_EW_SCALAR = 4, AB_EW_GCRT = 5, AB_EW_GINVCRT = 6 };
 void ab_launch_elementwise(const ab_plan *p, int op, const AbView &v, const int64_t *x, int64_t x_batch,

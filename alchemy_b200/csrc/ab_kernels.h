@@ -18,6 +18,8 @@ void ab_launch_hint_ip(const ab_plan *p, int64_t *out, int64_t out_bstride, cons
                        const int64_t *add, int64_t add_bstride, bool accumulate, int64_t batch, int32_t nlimbs, int32_t ndig, cudaStream_t st);
 // hints pre-multiplied by 2^32 / 2^48 (uint2 per residue), then the inner product with one reduction per output
 void ab_launch_hint_prep(const ab_plan *p, void *out, const int64_t *hint, int64_t rows, int32_t nlimbs, cudaStream_t st);
+// [ndig][2][L][n] int64 -> [ndig][L][n] uint2 (both components x 2^32) for k_crt_mixed_mac
+void ab_launch_hint_prep2(const ab_plan *p, void *out, const int64_t *hint, int64_t ndig, int32_t nlimbs, cudaStream_t st);
 void ab_launch_hint_ip_m(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *dig, int64_t dig_bstride, const void *hm,
                          const int64_t *add, int64_t add_bstride, int64_t batch, int32_t nlimbs, int32_t ndig, cudaStream_t st);
 void ab_launch_lin_ip(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *x, int64_t x_bstride, const int64_t *f,

@@ -7,6 +7,7 @@
 // caller-supplied scratch buffer that is sized to stay L2-resident (the batch is processed in
 // chunks).  All polynomials are in the CRT basis, PLANAR layout: c[b][i][l][j].
 #include <algorithm>
+#include <cstdlib>
 
 #include "ab_internal.h"
 #include "ab_kernels.h"
@@ -43,6 +44,11 @@ static void fill_digits(const ab_plan *p, int32_t nlimbs, int32_t base, AbMxFuse
 }
 static bool fused_ok(const ab_plan *p, int32_t nlimbs, const void *a, const void *b) {
     return !ab_pow2_supported(p) && ab_mixed_supported(p, AbView{(int64_t *)a, 1, 0, nlimbs, AB_LAYOUT_PLANAR}) && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+}
+
+static bool mac_ok(const ab_plan *p, int32_t nlimbs, const void *a, const void *b) {
+    static const bool off = getenv("AB_NO_MAC") && atoi(getenv("AB_NO_MAC")) != 0;      // A/B measurements only
+    return !off && fused_ok(p, nlimbs, a, b) && ab_mixed_mac_supported(p, nlimbs);
 }
 
 extern "C" int ab_ct_mul_dev(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, void *stream) {
@@ -152,6 +158,30 @@ extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int
         const int64_t chunk = chunk_of(batch, ks_item_words(p, nlimbs, nd) * 8);
         int64_t *hm = (int64_t *)work;                         // prepared hint: [nd][2][L][n] uint2
         int64_t *work2 = hm + (int64_t)nd * 2 * per;
+        if (batch > 0 && mac_ok(p, nlimbs, in3, work)) {
+            // two launches per chunk: crtInv of c2 straight out of the input, then the fused gadget inner product
+            // (digit extraction, forward CRT and multiply-accumulate on chip; ab_crt_mixed.cu k_crt_mixed_mac)
+            ab_launch_hint_prep2(p, hm, hint, nd, nlimbs, st);
+            const int64_t chunk2 = std::min(batch, std::max<int64_t>(1, chunk * (1 + (int64_t)nd) / 3));     // scratch: c2, running sums, centred source
+            for (int64_t b0 = 0; b0 < batch; b0 += chunk2) {
+                const int64_t B = std::min(chunk2, batch - b0);
+                int64_t *c2 = work2, *accs = c2 + B * per, *tb = accs + B * per;
+                const int64_t *in = in3 + b0 * 3 * per;
+                AbMxFused fi{};
+                fi.load_mode = AB_MX_LOAD_SRC; fi.src = in + 2 * per; fi.src_ustride = 3 * per; fi.src_limb0 = 0;
+                ab_launch_crt_mixed_fused(p, AbView{c2, B, 0, nlimbs, AB_LAYOUT_PLANAR}, true, &fi, st);
+                AbMxFused fx{};
+                fx.load_mode = AB_MX_LOAD_DIGITS;
+                fill_digits(p, nlimbs, base, fx, false);
+                fx.src = c2; fx.src_ustride = per; fx.n_src = (int32_t)n; fx.gK = 1;
+                if (base == 0) { fx.triv_src = in + 2 * per; fx.triv_ustride = 3 * per; }
+                AbMxMac mac{};
+                mac.hm = hm; mac.K = 1; mac.add = in; mac.add_ustride = 3 * per; mac.acc = accs; mac.tbuf = (1 + (int64_t)nd >= 3) ? tb : nullptr;
+                mac.out = out2 + b0 * 2 * per; mac.out_ustride = 2 * per;
+                ab_launch_crt_mixed_mac(p, B, nlimbs, fx, mac, st);
+            }
+            return;
+        }
         if (batch > 0) ab_launch_hint_prep(p, hm, hint, (int64_t)nd * 2, nlimbs, st);
         for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
             const int64_t B = std::min(chunk, batch - b0);
@@ -270,6 +300,40 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
         const int64_t chunk = chunk_of(batch, tn_item_words(t, nlimbs, nd) * 8);
         int64_t *hm = (int64_t *)work;               // prepared hint: [K][nd][2][L][n_s] uint2
         int64_t *work2 = hm + K * (int64_t)nd * 2 * per_s;
+        if (batch > 0 && mac_ok(ps, nlimbs, out2_s, work) && ((per_r * 8) % 16) == 0) {
+            ab_launch_hint_prep2(ps, hm, hint, K * (int64_t)nd, nlimbs, st);
+            // scratch per ciphertext without the digit buffers: 3 L n_r + (K + 3) L n_s words
+            const int64_t w_old = tn_item_words(t, nlimbs, nd), w_new = 3 * per_r + (K + 3) * per_s;
+            const int64_t chunk2 = std::min(batch, std::max<int64_t>(1, chunk * w_old / w_new));
+            for (int64_t b0 = 0; b0 < batch; b0 += chunk2) {
+                const int64_t B = std::min(chunk2, batch - b0);
+                int64_t *cin = work2;                    // [B][2][L][n_r]
+                int64_t *c0d = cin + B * 2 * per_r;      // [B][L][n_r]
+                int64_t *p0 = c0d + B * per_r;           // [B][K][L][n_s]
+                int64_t *lin = p0 + B * K * per_s;       // [B][L][n_s]
+                int64_t *accs = lin + B * per_s;         // [B][L][n_s] running sums of the fused inner product
+                int64_t *tb = accs + B * per_s;          // [B][L][n_s] centred source + H of the current (k, source limb)
+                ab_launch_copy_rows(cin, 2 * per_r, in2_r + b0 * 2 * per_r, 2 * per_r, 2 * per_r, B, st);
+                ab_crt_dispatch(pr, AbView{cin, B * 2, 0, nlimbs, AB_LAYOUT_PLANAR}, true, st);
+                ab_launch_copy_rows(c0d, per_r, cin, 2 * per_r, per_r, B, st);
+                ab_launch_prime_op(pr, AB_PR_LINV, AbView{c0d, B, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
+                ab_launch_tunnel_gather(ps, p0, c0d, per_r, nr, t->d_dec, t->d_dec_sgn, B, K, nlimbs, st);
+                ab_launch_prime_op(ps, AB_PR_L, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
+                ab_crt_dispatch(ps, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
+                ab_launch_lin_ip(ps, lin, per_s, p0, K * per_s, flin, B, nlimbs, (int32_t)K, st);
+                // c1: gather (coeffs . embed), gadget digit, reduction, forward CRT of O_s' and the inner product with
+                // the hint, all inside one kernel; the evalLin part of c0 is added on the way out
+                AbMxFused fx{};
+                fx.load_mode = AB_MX_LOAD_DIGITS;
+                fill_digits(ps, nlimbs, base, fx, false);
+                fx.src = cin + per_r; fx.src_ustride = 2 * per_r; fx.n_src = (int32_t)nr; fx.gather = t->d_pow; fx.gK = (int32_t)K;
+                AbMxMac mac{};
+                mac.hm = hm; mac.K = (int32_t)K; mac.add0 = lin; mac.add0_ustride = per_s; mac.acc = accs; mac.tbuf = tb;
+                mac.out = out2_s + b0 * 2 * per_s; mac.out_ustride = 2 * per_s;
+                ab_launch_crt_mixed_mac(ps, B, nlimbs, fx, mac, st);
+            }
+            return;
+        }
         if (batch > 0) ab_launch_hint_prep(ps, hm, hint, K * (int64_t)nd * 2, nlimbs, st);
         for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
             const int64_t B = std::min(chunk, batch - b0);
