@@ -330,20 +330,19 @@ __device__ __forceinline__ void mx_digit_from_t(const AbMxFused &fx, int d, int 
         // power-of-two base, inner digit: the wanted bits of floor(t / 2^s) sit in the low word of t (two's complement),
         // and |digit| <= b/2 < q needs no reduction
         const uint32_t mask = (uint32_t)gb - 1u;
-        const uint32_t *lo = reinterpret_cast<const uint32_t *>(tbuf);
-        for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {
-            uint32_t w[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) w[u] = (j0 + u * T < n) ? __ldcg(lo + 2 * (j0 + u * T)) : 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u * T;
-                if (j < n) {
-                    const int32_t c = (int32_t)((w[u] >> pw_shift) & mask) - hb;
-                    sm[j] = c < 0 ? q + (uint32_t)c : (uint32_t)c;
-                }
-            }
+        auto dig = [&](int lo) {
+            const int32_t c = (int32_t)(((uint32_t)lo >> pw_shift) & mask) - hb;
+            return c < 0 ? q + (uint32_t)c : (uint32_t)c;
+        };
+        // four consecutive positions per thread: two 16-byte loads of t, one 16-byte shared store
+        const int n4 = n >> 2;
+        const int4 *t4 = reinterpret_cast<const int4 *>(tbuf);
+        uint4 *s4 = reinterpret_cast<uint4 *>(sm);
+        for (int g = threadIdx.x; g < n4; g += T) {
+            const int4 a = __ldcg(t4 + 2 * g), b = __ldcg(t4 + 2 * g + 1);
+            s4[g] = make_uint4(dig(a.x), dig(a.z), dig(b.x), dig(b.z));
         }
+        for (int j = 4 * n4 + threadIdx.x; j < n; j += T) sm[j] = dig((int)__ldcg(tbuf + j));
         return;
     }
     for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {
@@ -491,7 +490,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
                     dst[i] = make_uint2((uint32_t)v.x, (uint32_t)v.z);
                 }
             } else if (tbuf) {
-                if (d == 0 || fx.dig[d].limb != fx.dig[d - 1].limb) mx_gather_centered(fx, d, unit, k, n, tbuf);
+                if (d == 0 || fx.dig[d].limb != fx.dig[d - 1].limb) {
+                    mx_gather_centered(fx, d, unit, k, n, tbuf);
+                    __syncthreads();      // the digit pass reads t with a different thread-to-position map
+                }
                 mx_digit_from_t(fx, d, n, q, tbuf, sm);
             } else {
                 mx_load_digit(fx, d, unit, k, n, q, sm);
@@ -502,31 +504,41 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
                 else run_program<false, false>(args, sm, tab, q, qinv_neg);
             }
             const uint2 *hp = hm + (int64_t)(k * fx.nd + d) * hstride;
-            const int T = blockDim.x;
-            for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {
-                uint2 h[4], a[4];
-                uint32_t x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + u * T;
-                    const bool in = j < n;
-                    h[u] = in ? __ldg(hp + j) : make_uint2(0, 0);
-                    a[u] = (in && !first) ? (ACC_SMEM ? acc[j] : __ldcg(acc + j)) : make_uint2(0, 0);
-                    x[u] = in ? sm[j] : 0u;
+            auto mac1 = [&](uint32_t x, uint32_t h0, uint32_t h1, uint32_t &a0, uint32_t &a1) {
+                const uint64_t t0 = (uint64_t)x * h0, t1 = (uint64_t)x * h1;
+                const uint32_t r0 = (uint32_t)((t0 + (uint64_t)((uint32_t)t0 * qinv_neg) * q) >> 32);
+                const uint32_t r1 = (uint32_t)((t1 + (uint64_t)((uint32_t)t1 * qinv_neg) * q) >> 32);
+                a0 = ab_addmod(ab_csub(r0, q), a0, q);
+                a1 = ab_addmod(ab_csub(r1, q), a1, q);
+            };
+            // four consecutive positions per thread and step: 16-byte loads of the hint pairs, the running sums and the
+            // residues; thread t owns the same positions for every digit (the sums need no synchronisation)
+            const int T = blockDim.x, n4 = n >> 2;
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(hp);
+            uint4 *a4 = reinterpret_cast<uint4 *>(acc);
+            const uint4 *x4 = reinterpret_cast<const uint4 *>(sm);
+            for (int g = threadIdx.x; g < n4; g += T) {
+                const uint4 ha = __ldg(h4 + 2 * g), hb2 = __ldg(h4 + 2 * g + 1);
+                uint4 aa = make_uint4(0, 0, 0, 0), ab2 = aa;
+                if (!first) {
+                    if (ACC_SMEM) { aa = a4[2 * g]; ab2 = a4[2 * g + 1]; }
+                    else { aa = __ldcg(a4 + 2 * g); ab2 = __ldcg(a4 + 2 * g + 1); }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + u * T;
-                    if (j < n) {
-                        const uint64_t t0 = (uint64_t)x[u] * h[u].x, t1 = (uint64_t)x[u] * h[u].y;
-                        uint32_t r0 = (uint32_t)((t0 + (uint64_t)((uint32_t)t0 * qinv_neg) * q) >> 32);
-                        uint32_t r1 = (uint32_t)((t1 + (uint64_t)((uint32_t)t1 * qinv_neg) * q) >> 32);
-                        r0 = ab_addmod(ab_csub(r0, q), a[u].x, q);      // a = 0 on the first digit
-                        r1 = ab_addmod(ab_csub(r1, q), a[u].y, q);
-                        if (ACC_SMEM) acc[j] = make_uint2(r0, r1);
-                        else __stcg(acc + j, make_uint2(r0, r1));
-                    }
-                }
+                const uint4 x = x4[g];
+                mac1(x.x, ha.x, ha.y, aa.x, aa.y);
+                mac1(x.y, ha.z, ha.w, aa.z, aa.w);
+                mac1(x.z, hb2.x, hb2.y, ab2.x, ab2.y);
+                mac1(x.w, hb2.z, hb2.w, ab2.z, ab2.w);
+                if (ACC_SMEM) { a4[2 * g] = aa; a4[2 * g + 1] = ab2; }
+                else { __stcg(a4 + 2 * g, aa); __stcg(a4 + 2 * g + 1, ab2); }
+            }
+            for (int j = 4 * n4 + threadIdx.x; j < n; j += T) {
+                const uint2 h = __ldg(hp + j);
+                uint2 a = make_uint2(0, 0);
+                if (!first) a = ACC_SMEM ? acc[j] : __ldcg(acc + j);
+                mac1(sm[j], h.x, h.y, a.x, a.y);
+                if (ACC_SMEM) acc[j] = a;
+                else __stcg(acc + j, a);
             }
             first = false;
             __syncthreads();       // the next digit overwrites sm
