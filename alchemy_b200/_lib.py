@@ -79,6 +79,11 @@ SIGNATURES = {
     "ab_tunnel_destroy": (None, [_vp]),
     "ab_tunnel_work_bytes": (_i64, [_vp, _i64, _i32, _i32]),
     "ab_tunnel_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "ab_ct_add_public_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "ab_ct_mul_public_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "ab_ct_phase_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "ab_rns_lift_reduce_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
+    "ab_lift_plain_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "ab_tensor_op_host": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int]),
     "ab_mul_host": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int]),
     "tensorCRTRq": (C.c_int, [C.c_int16, _vp, _i64, C.POINTER(PrimeExp), C.c_int16, C.POINTER(_vp), C.POINTER(_i64)]),

@@ -149,6 +149,9 @@ void ab_launch_prime_op(const ab_plan *p, int op, const AbView &v, cudaStream_t 
     for (size_t ai = 0; ai < p->axes.size(); ++ai) {
         const AbAxis &ax = p->axes[ai];
         if (ax.p == 2) continue;                 // L_2 and G_2 are the identity (g runs over odd primes)
+        if (op == AB_PR_GINVPOW || op == AB_PR_GINVDEC)
+            for (int l = 0; l < v.nlimbs; ++l)
+                AB_REQUIRE(p->limb[v.limb0 + l].pinv[ai] != 0, AB_ERR_UNSUPPORTED, "divG: a prime of m is not invertible modulo this modulus");
         (void)is_g;
         PrArgs a{};
         a.nlimbs = v.nlimbs; a.op = op; a.d = ax.p - 1; a.n = p->n; a.rts = ax.rts;

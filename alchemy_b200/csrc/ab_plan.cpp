@@ -348,6 +348,18 @@ static void build_generic(ab_plan *pl) {
     }
 }
 
+// inverse modulo any q >= 2 (extended Euclid), 0 when gcd(a, q) != 1
+static uint64_t inv_or_zero(uint64_t a, uint64_t q) {
+    int64_t r0 = (int64_t)q, r1 = (int64_t)(a % q), t0 = 0, t1 = 1;
+    while (r1 != 0) {
+        const int64_t k = r0 / r1;
+        int64_t t = r0 - k * r1; r0 = r1; r1 = t;
+        t = t0 - k * t1; t0 = t1; t1 = t;
+    }
+    if (r0 != 1) return 0;
+    return (uint64_t)((t0 % (int64_t)q + (int64_t)q) % (int64_t)q);
+}
+
 // ------------------------------------------------------------------------------------ plan
 static void plan_build(ab_plan *pl, const ab_prime_exp *pe, int32_t npe, const int64_t *moduli, int32_t L,
                        const int64_t *roots, bool want_crt) {
@@ -377,14 +389,19 @@ static void plan_build(ab_plan *pl, const ab_prime_exp *pe, int32_t npe, const i
     pl->has_crt = want_crt;
     for (int l = 0; l < L; ++l) {
         const int64_t q = moduli[l];
-        AB_REQUIRE(q > 2 && q < (1ll << 31) && is_prime((uint64_t)q), AB_ERR_ARG, "modulus must be an odd prime below 2^31");
-        for (auto &a : pl->axes) AB_REQUIRE(q != a.p, AB_ERR_ARG, "modulus divides m");
+        if (want_crt) {
+            AB_REQUIRE(q > 2 && q < (1ll << 31) && is_prime((uint64_t)q), AB_ERR_ARG, "modulus must be an odd prime below 2^31");
+            for (auto &a : pl->axes) AB_REQUIRE(q != a.p, AB_ERR_ARG, "modulus divides m");
+        } else {
+            // plaintext rings: any modulus (Z_7 in examples/Arithmetic.hs, Z_{2^k} in examples/HomomRLWR.hs)
+            AB_REQUIRE(q >= 2 && q < (1ll << 31), AB_ERR_ARG, "modulus must lie in [2, 2^31)");
+        }
         pl->q.push_back(q);
         AbLimbDev &ld = pl->limb[l];
         ld.q = (uint32_t)q;
         ld.mu = (uint64_t)(((unsigned __int128)1 << 64) / (uint64_t)q);
         for (size_t a = 0; a < pl->axes.size(); ++a) {
-            uint64_t pi = invmod(pl->axes[a].p % q, q);
+            uint64_t pi = inv_or_zero((uint64_t)pl->axes[a].p % (uint64_t)q, (uint64_t)q);   // 0: p not invertible mod q (divG refuses)
             ld.pinv[a] = (uint32_t)pi;
             ld.pinv_s[a] = shoup(pi, q);
         }

@@ -61,7 +61,8 @@ const char *ab_version(void);
  * omega_m = g^((q-1)/m) with g the smallest generator of Z_q^* (Lol `principalRootUnity`).
  * Fails with AB_ERR_NO_ROOT if some q has no m-th root of unity: then only the non-CRT entries
  * (L, G in Pow/Dec, twace/embed Pow/Dec, pointwise) may be used on a plan created with
- * ab_plan_create_nocrt. */
+ * ab_plan_create_nocrt.  A nocrt plan also accepts composite moduli 2 <= q < 2^31 (plaintext rings Z_p, p = 2^k
+ * in examples/HomomRLWR.hs): divG then needs every odd prime of m invertible mod q (AB_ERR_UNSUPPORTED otherwise). */
 int ab_plan_create(ab_plan **out, const ab_prime_exp *pe, int32_t num_pe,
                    const int64_t *moduli, int32_t num_limbs, const int64_t *roots);
 int ab_plan_create_nocrt(ab_plan **out, const ab_prime_exp *pe, int32_t num_pe,
@@ -159,6 +160,28 @@ void ab_tunnel_destroy(ab_tunnel *t);
 int64_t ab_tunnel_work_bytes(const ab_tunnel *t, int64_t batch, int32_t nlimbs, int32_t base);
 int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t *in2_r, const int64_t *flin, const int64_t *hint,
                   int64_t batch, int32_t nlimbs, int32_t base, void *work, void *stream);
+
+/* ---- the ciphertext <-> plaintext boundary of SymmSHE (upstream: Haskell over Cyc values [RECALL]) ------------
+ * All PLANAR; ciphertexts c[b][i][l][j] in the CRT basis over the first `nlimbs` moduli of the plan. */
+
+/* addPublic / mulPublic cores (Eval.hs:131-132): `pub`[l][j] is the public ring element already brought to the
+ * ciphertext's form (embedded into O_m', reduced mod every q_l, times g^k / scaled by l^-1, CRT basis):
+ *   add: c[b][0] += pub        mul: c[b][i] *= pub for every i < npoly */
+int ab_ct_add_public_dev(const ab_plan *p, int64_t *c, const int64_t *pub, int64_t batch, int32_t npoly, int32_t nlimbs, void *stream);
+int ab_ct_mul_public_dev(const ab_plan *p, int64_t *c, const int64_t *pub, int64_t batch, int32_t npoly, int32_t nlimbs, void *stream);
+
+/* `evaluate c s` of Lol's errorTermUnrestricted / decrypt (PT2CT.hs:99, Eval.hs:155-160):
+ *   out[b][l][j] = sum_i c[b][i][l][j] * s[l][j]^i     (s = the secret key reduced mod q, CRT basis) */
+int ab_ct_phase_dev(const ab_plan *p, int64_t *out, const int64_t *c, const int64_t *s, int64_t batch, int32_t npoly, int32_t nlimbs, void *stream);
+
+/* `reduce . lift` across the RNS product, per coefficient (any basis):  x = centred representative of in[b][.][j]
+ * modulo Q = q_0 ... q_(nlimbs-1), in (-Q/2, Q/2);  out[b][j] = x mod pmod in [0, pmod).
+ * maxrate (may be NULL): maxrate[b] = max_j |x| / Q as a double -- ALCHEMY's errorRate (Eval.hs:155-160). */
+int ab_rns_lift_reduce_dev(const ab_plan *p, int64_t *out, double *maxrate, const int64_t *in, int64_t batch, int32_t nlimbs, int64_t pmod, void *stream);
+
+/* plaintext side of encrypt / addPublic / mulPublic: out[b][l][j] = lift_pmod(in[b][j]) mod q_l, with Lol's
+ * `lift` = the representative in [-pmod/2, pmod/2).  `in` holds one coefficient vector (n of the plan) per b. */
+int ab_lift_plain_dev(const ab_plan *p, int64_t *out, const int64_t *in, int64_t batch, int32_t nlimbs, int64_t pmod, void *stream);
 
 /* ---- host-buffer entries: what a `foreign import ccall` from Lol's CPP.hs would bind ------------
  * lol-cpp shape [RECALL]: void tensorCRTRq(hShort_t tupSize, Zq* y, hDim_t totm, PrimeExponent* pe,

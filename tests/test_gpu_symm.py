@@ -1,0 +1,123 @@
+"""GPU parity for the SymmSHE boundary (alchemy_b200/symm.py over the C ABI) against oracle/symm_oracle.py, stage by
+stage and bit for bit, on the circuit of examples/Arithmetic.hs -- addMul = \\x y -> (x + y) * y compiled as
+PT2CT.hs:172-177 prescribes -- plus addPublic / mulPublic / modSwitchPT / errorRate, ending in the reference's own
+criterion: decrypt (eval ct) == eval pt (examples/Arithmetic.hs:75)."""
+import numpy as np
+import pytest
+
+from oracle import she_oracle as S
+from oracle import symm_oracle as Y
+from test_symm_oracle import ARITH_Q, plain_mul, primes_1_mod
+
+pytestmark = pytest.mark.gpu
+
+RLWR_Q = [1543651201, 689270401, 718099201, 720720001, 1556755201, 1567238401]
+
+
+def dev(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).cuda()
+
+
+def same(got, want):
+    return (got.cpu().numpy() == want).all()
+
+
+CASES = [  # m, m', moduli, p, L_in, L_hint, L_out, gadget base
+    (4, 512, ARITH_Q, 7, 2, 2, 1, 0),                       # examples/Arithmetic.hs with its limb schedule
+    (4, 16, primes_1_mod(16, 1 << 22, 3), 7, 2, 3, 1, 0),
+    (3, 45, primes_1_mod(45, 1 << 24, 3), 4, 2, 2, 1, 2),   # odd primes in m': g != 1, mulG / divG on the decrypt side
+    (9, 63, primes_1_mod(63, 1 << 24, 3), 8, 2, 3, 1, 4),
+    (4095, 20475, RLWR_Q, 2, 2, 3, 1, 0),                   # HomomRLWR's last ring pair H5 -> H5' (Common.hs:52-54), Z_2 plaintexts
+]
+
+
+@pytest.mark.parametrize("m,mp,moduli,p,lin,lh,lout,base", CASES)
+def test_arithmetic_circuit_stage_by_stage(m, mp, moduli, p, lin, lh, lout, base):
+    from alchemy_b200 import symm
+    rng = np.random.default_rng(m * 131 + mp)
+    ora, gpu = Y.SymmSHE(m, mp, moduli, p), symm.SymmSHE(m, mp, moduli, p)
+    B, n, np_ = 2, ora.n, ora.np_
+    s_dec = rng.integers(-1, 2, size=np_)
+    sk_o, sk_g = ora.gen_sk(s_dec), gpu.genSK(dev(s_dec))
+    assert same(sk_g, sk_o)
+
+    def enc(L):
+        mu, noise = rng.integers(0, p, size=(B, n)), rng.integers(-2, 3, size=(B, np_))
+        c1 = np.stack([rng.integers(0, q, size=(B, np_)) for q in moduli[:L]], axis=1)
+        co, cg = ora.encrypt(sk_o, mu, noise, c1), gpu.encrypt(sk_g, dev(mu), dev(noise), dev(c1))
+        assert same(cg.c, co.c)
+        return mu, co, cg
+
+    x, xo, xg = enc(lin)
+    y, yo, yg = enc(lin)
+    assert same(gpu.decrypt(sk_g, xg), x) and (ora.decrypt(sk_o, xo) == x).all()
+    D = S.gadget_len(moduli[:lh], base)
+    mask = np.stack([rng.integers(0, q, size=(D, np_)) for q in moduli[:lh]], axis=1)
+    hnoise = rng.integers(-1, 2, size=(D, np_))
+    hint_o, hint_g = ora.ks_hint(sk_o, mask, hnoise, lh, base), gpu.ksQuadCircHint(sk_g, dev(mask), dev(hnoise), lh, base)
+    assert same(hint_g, hint_o)
+
+    so, sg = ora.add(xo, yo), gpu.add(xg, yg)
+    assert same(sg.c, so.c)
+    po, pg = ora.mul(so, yo), gpu.mul(sg, yg)
+    assert same(pg.c, po.c) and (pg.k, pg.l, pg.enc) == (po.k, po.l, po.enc)
+    want = np.stack([plain_mul(m, p, ((a + b) % p)[None], b[None])[0] for a, b in zip(x, y)])
+    assert same(gpu.decrypt(sk_g, pg), want)                 # degree-2 ciphertext, k = 1: divG on the way out
+    for step_o, step_g in ((lambda c: ora.mod_switch(c, lh), lambda c: gpu.modSwitch(c, lh)),
+                           (lambda c: ora.key_switch_quad(c, hint_o, base), lambda c: gpu.keySwitchQuad(c, hint_g, base)),
+                           (lambda c: ora.mod_switch(c, lout), lambda c: gpu.modSwitch(c, lout))):
+        po, pg = step_o(po), step_g(pg)
+        assert same(pg.c, po.c) and (pg.k, pg.l, pg.enc) == (po.k, po.l, po.enc)
+    assert tuple(pg.c.shape[1:3]) == (2, lout)
+    got = gpu.decrypt(sk_g, pg)
+    assert same(got, ora.decrypt(sk_o, po)) and same(got, want)        # the reference's PASS criterion
+    rate_g, rate_o = gpu.errorRate(sk_g, pg).cpu().numpy(), ora.error_rate(sk_o, po)
+    assert np.allclose(rate_g, rate_o, rtol=1e-9, atol=0) and (rate_g < 0.25).all()
+
+    # (x + y) * y + x: aligning a fresh ciphertext (k = 0, LSD) with the evaluated one; addPublic / mulPublic
+    xo1, xg1 = ora.mod_switch(xo, lout), gpu.modSwitch(xg, lout)
+    ao, ag = ora.add(po, xo1), gpu.add(pg, xg1)
+    assert same(ag.c, ao.c) and same(gpu.decrypt(sk_g, ag), (want + x) % p)
+    pub = rng.integers(0, p, size=n)
+    bo, bg = ora.add_public(po, pub), gpu.addPublic(pg, dev(pub))
+    assert same(bg.c, bo.c) and same(gpu.decrypt(sk_g, bg), (want + pub) % p)
+    mo, mg = ora.mul_public(xo, pub), gpu.mulPublic(xg, dev(pub))
+    want_pub = np.stack([plain_mul(m, p, a[None], pub[None])[0] for a in x])
+    assert same(mg.c, mo.c) and same(gpu.decrypt(sk_g, mg), want_pub)
+
+
+def test_mod_switch_pt_and_rns_lift_edges():
+    """div2_ (Eval.hs:95) through the device path; centred lift at the extremes of the RNS range"""
+    import ctypes as C
+
+    import torch
+
+    import alchemy_b200 as ab
+    from alchemy_b200 import symm
+    m, mp, p, p2 = 3, 45, 8, 4
+    moduli = primes_1_mod(45, 1 << 24, 3)
+    rng = np.random.default_rng(11)
+    ora, gpu = Y.SymmSHE(m, mp, moduli, p), symm.SymmSHE(m, mp, moduli, p)
+    s_dec = rng.integers(-1, 2, size=ora.np_)
+    sk_o, sk_g = ora.gen_sk(s_dec), gpu.genSK(dev(s_dec))
+    mu = 2 * rng.integers(0, p2, size=(2, ora.n))
+    noise = rng.integers(-2, 3, size=(2, ora.np_))
+    c1 = np.stack([rng.integers(0, q, size=(2, ora.np_)) for q in moduli[:2]], axis=1)
+    cg = gpu.modSwitchPT(gpu.encrypt(sk_g, dev(mu), dev(noise), dev(c1)), p2)
+    co = ora.mod_switch_pt(ora.encrypt(sk_o, mu, noise, c1), p2)
+    assert same(cg.c, co.c) and cg.l == co.l
+    assert same(symm.SymmSHE(m, mp, moduli, p2).decrypt(sk_g, cg), mu // 2)
+    # centred lift: 0, +-1, +-(Q-1)/2 and random residues, for 1..3 limbs, against python integers
+    plan = ab.Plan(mp, moduli)
+    for L in (1, 2, 3):
+        q = moduli[:L]
+        Q = int(np.prod([int(v) for v in q], dtype=object))
+        vals = [0, 1, -1, (Q - 1) // 2, -((Q - 1) // 2), (Q - 1) // 2 - 1, 12345, -98765] + [int(rng.integers(0, 1 << 62)) % Q - Q // 2 for _ in range(plan.n - 8)]
+        x = np.array([[v % ql for v in vals] for ql in q], dtype=np.int64)[None]
+        for pmod in (2, 7, 32, (1 << 31) - 1):
+            out = torch.empty((1, plan.n), dtype=torch.int64, device="cuda")
+            rate = torch.zeros(1, dtype=torch.float64, device="cuda")
+            ab.check(ab.lib().ab_rns_lift_reduce_dev(plan.h, C.c_void_p(out.data_ptr()), C.c_void_p(rate.data_ptr()), C.c_void_p(dev(x).data_ptr()), 1, L, pmod, None))
+            assert out.cpu().numpy()[0].tolist() == [v % pmod for v in vals]
+            assert abs(rate.item() - max(abs(v) for v in vals) / Q) < 1e-12
