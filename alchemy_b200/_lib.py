@@ -84,6 +84,8 @@ SIGNATURES = {
     "ab_ct_phase_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "ab_rns_lift_reduce_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "ab_lift_plain_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
+    "ab_uniform_dev": (C.c_int, [_vp, _vp, _i64, _i32, C.c_uint64, C.c_uint32, _vp]),
+    "ab_gaussian_dev": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_uint64), _i32, C.c_uint64, C.c_uint32, _vp]),
     "ab_tensor_op_host": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int]),
     "ab_mul_host": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int]),
     "tensorCRTRq": (C.c_int, [C.c_int16, _vp, _i64, C.POINTER(PrimeExp), C.c_int16, C.POINTER(_vp), C.POINTER(_i64)]),

@@ -3,7 +3,7 @@ scalar l) around the device kernels.  Reference call sites: encrypt / decrypt Cr
 PT2CT.hs:78-99; add_/mul_ Eval.hs:58-67; modSwitchPT_/modSwitch_/addPublic_/mulPublic_/keySwitchQuad_
 Eval.hs:129-133; errorRate_ Eval.hs:155-160; hint generation Crypto/Alchemy/Interpreter/KeysHints.hs:96,113.
 SymmSHE itself lives in the absent `lol-apps` package ([RECALL]); the conventions this
-file fixes are listed in oracle/symm_oracle.py, which restates the same operations on the CPU.
+file fixes (S1-S7) are listed in DESIGN.md section 8; the test suite restates the same operations on the CPU.
 
 Every ring operation below is a CUDA kernel behind the C ABI; Python only carries the three scalars
 (enc, k, l) per ciphertext *type* -- in ALCHEMY they are compile-time data of the typed DSL.
@@ -97,6 +97,19 @@ class SymmSHE:
                 GT.add(self.hi, h0[d, l].view(1, 1, n), g, limb0=l, nlimbs=1)
                 d += 1
         return torch.stack([h0, mask], dim=1).contiguous()
+
+    # ---- the same with device randomness (KeysHints.hs:96 getKey / genSK, :113 getQuadCircHint) -------------------
+    # stream ids: 0 secret key, 1 encryption noise, 2 encryption mask, 3 hint noise, 4 hint mask
+    def sampleSK(self, cdt, seed):
+        return self.genSK(GT.gaussianDec(self.hi, 1, cdt, seed, 0)[0])
+
+    def sampleKSQuadCircHint(self, sk, L, cdt, seed, base=0):
+        D = GT.gadgetLen(self.hi, L, base)
+        return self.ksQuadCircHint(sk, GT.uniform(self.hi, D, L, seed, 4), GT.gaussianDec(self.hi, D, cdt, seed, 3), L, base)
+
+    def encryptRandom(self, sk, mu, L, cdt, seed):
+        B = mu.shape[0]
+        return self.encrypt(sk, mu, GT.gaussianDec(self.hi, B, cdt, seed, 1), GT.uniform(self.hi, B, L, seed, 2))
 
     # ---- encrypt / decrypt ---------------------------------------------------------------------
     def encrypt(self, sk, mu, noise_dec, c1):

@@ -233,6 +233,23 @@ class GT:
         check(lib().ab_rescale_drop_dev(plan.h, _ptr(out), _ptr(x), b, nl, d, _stream()))
         return out
 
+    # ---- randomness (Lol `tGaussianDec`, MonadRandom draws of KeysHints.hs:96,113) ------------------
+    @staticmethod
+    def uniform(plan, batch, nlimbs, seed, stream_id, device="cuda"):
+        """[batch, L, n] residues uniform in [0, q_l): Philox4x32-10 at (seed, stream_id, position)"""
+        out = torch.empty((batch, nlimbs, plan.n), dtype=torch.int64, device=device)
+        check(lib().ab_uniform_dev(plan.h, _ptr(out), batch, nlimbs, seed, stream_id, _stream()))
+        return out
+
+    @staticmethod
+    def gaussianDec(plan, batch, cdt, seed, stream_id, device="cuda"):
+        """[batch, n] signed integers from the discrete Gaussian whose folded cumulative table is `cdt`
+        (floor(2^64 P(|X| <= k)), k = 0, 1, ...), i.i.d. per decoding-basis coefficient"""
+        out = torch.empty((batch, plan.n), dtype=torch.int64, device=device)
+        tab = (C.c_uint64 * len(cdt))(*[int(t) for t in cdt])
+        check(lib().ab_gaussian_dev(plan.h, _ptr(out), batch, tab, len(cdt), seed, stream_id, _stream()))
+        return out
+
     # ---- host-buffer entry (what a Haskell foreign import would call) ------------------------
     @staticmethod
     def hostOp(plan, op, y_host, layout=INTERLEAVED):

@@ -183,6 +183,14 @@ int ab_rns_lift_reduce_dev(const ab_plan *p, int64_t *out, double *maxrate, cons
  * `lift` = the representative in [-pmod/2, pmod/2).  `in` holds one coefficient vector (n of the plan) per b. */
 int ab_lift_plain_dev(const ab_plan *p, int64_t *out, const int64_t *in, int64_t batch, int32_t nlimbs, int64_t pmod, void *stream);
 
+/* ---- randomness for keys and hints (KeysHints.hs:96,113,115-129; upstream: Haskell MonadRandom + tGaussianDec) --
+ * Counter-based (Philox4x32-10): every value is a function of (seed, stream_id, position) only.
+ *   ab_uniform_dev : out[b][l][j] uniform in [0, q_l)
+ *   ab_gaussian_dev: out[b][j] signed integers, |x| = #{k : cdt[k] <= u} for a uniform 64-bit u, with
+ *                    cdt[k] = floor(2^64 P(|X| <= k)) (HOST array, non-decreasing, at most 128 entries) */
+int ab_uniform_dev(const ab_plan *p, int64_t *out, int64_t batch, int32_t nlimbs, uint64_t seed, uint32_t stream_id, void *stream);
+int ab_gaussian_dev(const ab_plan *p, int64_t *out, int64_t batch, const uint64_t *cdt, int32_t cdt_len, uint64_t seed, uint32_t stream_id, void *stream);
+
 /* ---- host-buffer entries: what a `foreign import ccall` from Lol's CPP.hs would bind ------------
  * lol-cpp shape [RECALL]: void tensorCRTRq(hShort_t tupSize, Zq* y, hDim_t totm, PrimeExponent* pe,
  *                                         hShort_t sizeOfPE, Zq** ru, hInt_t* qs)

@@ -121,3 +121,33 @@ def test_mod_switch_pt_and_rns_lift_edges():
             ab.check(ab.lib().ab_rns_lift_reduce_dev(plan.h, C.c_void_p(out.data_ptr()), C.c_void_p(rate.data_ptr()), C.c_void_p(dev(x).data_ptr()), 1, L, pmod, None))
             assert out.cpu().numpy()[0].tolist() == [v % pmod for v in vals]
             assert abs(rate.item() - max(abs(v) for v in vals) / Q) < 1e-12
+
+
+def test_device_randomness_matches_the_cpu_restatement_and_drives_the_circuit():
+    """keys, hint and encryptions drawn on the device (Philox4x32-10), bit-identical to oracle/rng_oracle.py, and the
+    addMul circuit of examples/Arithmetic.hs still decrypts to the plaintext result"""
+    import alchemy_b200 as ab
+    from alchemy_b200 import symm
+    from oracle import rng_oracle as R
+    m, mp, moduli, p, lin, lh, lout = 4, 512, ARITH_Q, 7, 2, 2, 1
+    gpu, ora = symm.SymmSHE(m, mp, moduli, p), Y.SymmSHE(m, mp, moduli, p)
+    cdt = R.gaussian_cdt(3.0 ** 0.5)                     # evalKeysHints (3.0 :: Double), examples/Arithmetic.hs:50
+    seed = 0x5eed5eed12345678
+    for stream_id, batch in ((2, 3), (4, 2)):
+        assert same(ab.GT.uniform(gpu.hi, batch, lin, seed, stream_id), R.uniform(moduli[:lin], batch, ora.np_, seed, stream_id))
+    assert same(ab.GT.uniform(gpu.hi, 1, 3, 7, 9), R.uniform(moduli, 1, ora.np_, 7, 9))
+    for stream_id, batch in ((0, 1), (1, 5), (3, 2)):
+        assert same(ab.GT.gaussianDec(gpu.hi, batch, cdt, seed, stream_id), R.gaussian(cdt, batch, ora.np_, seed, stream_id))
+    sk = gpu.sampleSK(cdt, seed)
+    assert same(sk, ora.gen_sk(R.gaussian(cdt, 1, ora.np_, seed, 0)[0]))
+    hint = gpu.sampleKSQuadCircHint(sk, lh, cdt, seed)
+    D = S.gadget_len(moduli[:lh], 0)
+    assert same(hint, ora.ks_hint(sk.cpu().numpy(), R.uniform(moduli[:lh], D, ora.np_, seed, 4), R.gaussian(cdt, D, ora.np_, seed, 3), lh, 0))
+    rng = np.random.default_rng(3)
+    x, y = rng.integers(0, p, size=(4, ora.n)), rng.integers(0, p, size=(4, ora.n))
+    cx, cy = gpu.encryptRandom(sk, dev(x), lin, cdt, seed), gpu.encryptRandom(sk, dev(y), lin, cdt, seed + 1)
+    ct = gpu.mul(gpu.add(cx, cy), cy)
+    ct = gpu.modSwitch(gpu.keySwitchQuad(gpu.modSwitch(ct, lh), hint), lout)
+    want = np.stack([plain_mul(m, p, ((a + b) % p)[None], b[None])[0] for a, b in zip(x, y)])
+    assert same(gpu.decrypt(sk, ct), want)
+    assert (gpu.errorRate(sk, ct).cpu().numpy() < 0.25).all()
