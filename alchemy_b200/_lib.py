@@ -75,6 +75,8 @@ SIGNATURES = {
     "ab_mod_switch_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "ab_key_switch_work_bytes": (_i64, [_vp, _i64, _i32, _i32]),
     "ab_key_switch_quad_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "ab_mul_key_switch_work_bytes": (_i64, [_vp, _i64, _i32, _i32, _i32, _i32]),
+    "ab_mul_key_switch_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ab_tunnel_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, _vp]),
     "ab_tunnel_destroy": (None, [_vp]),
     "ab_tunnel_work_bytes": (_i64, [_vp, _i64, _i32, _i32]),

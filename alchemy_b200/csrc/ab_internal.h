@@ -101,6 +101,8 @@ struct AbLimbDev {
     const uint2_ *tw_fwd;        // pow2 path: merged negacyclic twiddles, window-packed (see above)
     const uint2_ *tw_inv;        // pow2 path: their inverses
     uint2_ tw0_fwd[32], tw0_inv[32];   // host copies of window 0 (same for every thread): passed as kernel constants
+    const uint2_ *tw_fwd_flat = nullptr; // pow2 path: the same twiddles unpacked, entry [2^s + l] (ab_mulks_pow2.cu)
+    const uint2_ *tw_inv_flat = nullptr;
     const uint2_ *gen_fwd;       // generic path: per-limb table block (matrices, twiddles)
     const uint2_ *gen_inv;
     const uint2_ *g_crt;         // g at every CRT row (Shoup pairs), n entries
@@ -254,6 +256,10 @@ bool ab_mixed_supported(const ab_plan *p, const AbView &v);       // ab_crt_mixe
 void ab_launch_crt_mixed(const ab_plan *p, const AbView &v, bool inverse, cudaStream_t st);
 void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, const AbMxFused *fx, cudaStream_t st);
 // units x nlimbs CTAs; fx describes the digit source (load_mode AB_MX_LOAD_DIGITS); plan p = the ring the digits live in
+// whole PT2CT mul_ pipeline in one kernel for small power-of-two rings with TrivGad (ab_mulks_pow2.cu)
+bool ab_mulks_pow2_supported(const ab_plan *p, int32_t lin, int32_t lh, int32_t lout, int32_t base);
+void ab_launch_mulks_pow2(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
+                          int32_t lin, int32_t lh, int32_t lout, cudaStream_t st);
 bool ab_mixed_mac_supported(const ab_plan *p, int32_t nlimbs);
 int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs);
 void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, const AbMxFused &fx, const AbMxMac &mac, cudaStream_t st);

@@ -204,6 +204,9 @@ static void build_pow2_tables(ab_plan *pl, int limb, AbLimbDev &ld) {
     }
     ld.ninv = (uint32_t)ninv;
     ld.ninv_s = shoup(ninv, q);
+    // unpacked copies (tw[2^s + l]) for the shared-memory transforms of the fused mul + key-switch kernel
+    ld.tw_fwd_flat = dev_upload(pl, fwd);
+    ld.tw_inv_flat = dev_upload(pl, inv);
 }
 
 // ------------------------------------------------------------------------------------ generic program

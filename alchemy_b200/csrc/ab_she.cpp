@@ -374,3 +374,41 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
         }
     });
 }
+
+// ------------------------------------------------------------------------------------ PT2CT mul_ as one entry
+// modSwitch (to l_out) . keySwitchQuad hint . modSwitch (to l_hint) . (*)   -- Crypto/Alchemy/Interpreter/PT2CT.hs:172-177.
+// Small power-of-two rings with TrivGad run as ONE kernel with every intermediate in shared memory
+// (ab_mulks_pow2.cu); everything else as the sequence of the entries above, intermediates in `work`.
+static int64_t mks_inter_words(const ab_plan *p, int64_t batch, int32_t lin, int32_t lh) {
+    return batch * p->n * (3 * (int64_t)lin + 3 * (int64_t)lh + 2 * (int64_t)lh);
+}
+extern "C" int64_t ab_mul_key_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t lin, int32_t lh, int32_t lout, int32_t base) {
+    if (!p || batch < 0 || lin < 1 || lh < 1 || lout < 1 || lin > p->L || lh > p->L || lout > p->L) return -1;
+    if (ab_mulks_pow2_supported(p, lin, lh, lout, base)) return 16;
+    const int64_t w1 = ab_mod_switch_work_bytes(p, batch, 3, lin, lh), w2 = ab_key_switch_work_bytes(p, batch, lh, base),
+                  w3 = ab_mod_switch_work_bytes(p, batch, 2, lh, lout);
+    if (w1 < 0 || w2 < 0 || w3 < 0) return -1;
+    return mks_inter_words(p, batch, lin, lh) * 8 + std::max(w1, std::max(w2, w3)) + 64;
+}
+extern "C" int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
+                                     int32_t lin, int32_t lh, int32_t lout, int32_t base, void *work, void *stream) {
+    return ab_guard([&] {
+        AB_REQUIRE(p && ((out2 && a2 && b2 && hint) || batch == 0), AB_ERR_ARG, "null argument");
+        AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan has no CRT tables");
+        AB_REQUIRE(batch >= 0 && lin >= 1 && lh >= 1 && lout >= 1 && lin <= p->L && lh <= p->L && lout <= p->L, AB_ERR_ARG, "bad batch or limb counts");
+        if (batch == 0) return;
+        if (ab_mulks_pow2_supported(p, lin, lh, lout, base)) {
+            ab_launch_mulks_pow2(p, out2, a2, b2, hint, batch, lin, lh, lout, (cudaStream_t)stream);
+            return;
+        }
+        AB_REQUIRE(work != nullptr, AB_ERR_ARG, "null scratch buffer");
+        const int64_t n = p->n;
+        int64_t *c3 = (int64_t *)work, *c3h = c3 + batch * 3 * lin * n, *c2h = c3h + batch * 3 * lh * n;
+        void *w = c2h + batch * 2 * lh * n;
+        auto must = [](int rc) { if (rc != AB_OK) throw ab_error{rc, ab_last_error()}; };
+        must(ab_ct_mul_dev(p, c3, a2, b2, batch, lin, stream));
+        must(ab_mod_switch_dev(p, c3h, c3, batch, 3, lin, lh, w, stream));
+        must(ab_key_switch_quad_dev(p, c2h, c3h, hint, batch, lh, base, w, stream));
+        must(ab_mod_switch_dev(p, out2, c2h, batch, 2, lh, lout, w, stream));
+    });
+}

@@ -53,10 +53,13 @@ def keySwitchQuadCirc(plan: Plan, c3, hint, base=0):
 def mulKeySwitch(plan: Plan, a, b, hint, l_hint, l_out, base=0):
     """PT2CT `mul_` (PT2CT.hs:172-177): modSwitch . keySwitchQuad hint . modSwitch . (*)
     a, b at L_in limbs; the hint lives at l_hint limbs; the result at l_out limbs."""
-    c3 = ctMul(plan, a, b)
-    c3 = modSwitch(plan, c3, l_hint)
-    c2 = keySwitchQuadCirc(plan, c3, hint, base)
-    return modSwitch(plan, c2, l_out)
+    B, two, lin, n = a.shape
+    assert two == 2 and b.shape == a.shape and n == plan.n and hint.shape[2] == l_hint
+    out = torch.empty((B, 2, l_out, n), dtype=torch.int64, device=a.device)
+    work = _work(lib().ab_mul_key_switch_work_bytes(plan.h, B, lin, l_hint, l_out, base), a.device)
+    check(lib().ab_mul_key_switch_dev(plan.h, _ptr(out), _ptr(a), _ptr(b), _ptr(hint), B, lin, l_hint, l_out, base,
+                                      C.c_void_p(work.data_ptr()), _stream()))
+    return out
 
 
 class Tunnel:

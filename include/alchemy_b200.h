@@ -149,6 +149,14 @@ int64_t ab_key_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t nlimbs
 int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int64_t *in3, const int64_t *hint,
                            int64_t batch, int32_t nlimbs, int32_t base, void *work, void *stream);
 
+/* PT2CT `mul_` (PT2CT.hs:172-177) as one call:  modSwitch(l_out) . keySwitchQuad hint . modSwitch(l_hint) . (*)
+ * a2, b2: [batch][2][l_in][n]; hint: [gadget_len(l_hint)][2][l_hint][n]; out2: [batch][2][l_out][n].
+ * Power-of-two rings that fit shared memory (examples/Arithmetic.hs: m' = 512) with TrivGad run as a single
+ * kernel, every intermediate on chip; all other cases as the sequence of the entries above. */
+int64_t ab_mul_key_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t l_in, int32_t l_hint, int32_t l_out, int32_t base);
+int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
+                          int32_t l_in, int32_t l_hint, int32_t l_out, int32_t base, void *work, void *stream);
+
 /* tunnel (Eval.hs:134): ring switch O_r' -> O_s' through E' = O_e'.
  *   c0' = sum_k embed(coeffsDec(c0)_k) * flin_k            (evalLin of the E'-linear function)
  *   (c0'',c1'') = sum_k sum_d reduce(decompose(embed(coeffsPow(c1)_k)))_d * hint_{k,d}

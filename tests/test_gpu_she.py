@@ -58,6 +58,15 @@ MULS = [  # (m, moduli, L_in, L_hint, L_out, base): the limb schedule of SURVEY.
     (36, [37, 73, 109], 2, 2, 1, 2),        # binary gadget, mixed-radix ring
     (11648, TUNNEL_Q, 2, 2, 1, 2),          # Tunnel.hs ring with its BaseBGad 2
     (20475, RLWR_Q, 2, 2, 1, 16),
+    # power-of-two rings, TrivGad: the single-kernel pipeline (ab_mulks_pow2.cu) incl. scale-up and multi-limb drops
+    (64, [193, 257, 449, 577, 641], 2, 4, 1, 0),
+    (64, [193, 257, 449, 577, 641], 3, 5, 2, 0),
+    (64, [193, 257, 449], 1, 2, 1, 0),
+    (64, [193, 257, 449], 3, 3, 3, 0),
+    (4, [1073479681, 1052835841], 1, 2, 1, 0),          # n = 2
+    (1024, [1073479681, 1052835841, 1032192001], 2, 3, 1, 0),
+    (2048, [1073479681, 1052835841, 1032192001], 2, 3, 2, 0),
+    (8192, [1073479681, 1052835841, 1032192001], 2, 3, 1, 0),   # too large for shared memory: the launch sequence behind the same entry
 ]
 
 
