@@ -306,9 +306,13 @@ def main():
                "api": "ab_tensor_op_host(CRT) + ab_tensor_op_host(CRT_INV), pinned host buffers"}
 
     # ---- secondary metric M2 (rank 0, N = 1 only): ciphertext mul + key-switch pipelines per second
-    m2 = None
+    m2 = m3 = None
     if rank == 0 and world == 1 and not args.no_m2:
         m2 = mul_keyswitch_leg(ab, torch)
+        # M3: the ring-tunnelling chain of examples/Tunnel.hs on a slice of the 4096-ciphertext workload (tools/bench_she.py)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from bench_she import tunnel_chain
+        m3 = tunnel_chain(1024, 2, 0, 1)
 
     # ---- gather a checksum of every rank's result over NCCL (the only collective of the path)
     if world > 1:
@@ -334,6 +338,8 @@ def main():
             line["e2e"] = e2e
         if m2:
             line["mul_keyswitch"] = m2
+        if m3:
+            line["tunnel_chain"] = m3
         if not args.no_cpu:
             line["cpu_baseline"], _ = cpu_leg(m, n, moduli, target_s=10.0)
         print(json.dumps(line), flush=True)
