@@ -398,6 +398,34 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
             return;
         }
         mx_load_digit(fx, d, fx.gK > 1 ? unit / fx.gK : unit, fx.gK > 1 ? (int)(unit % fx.gK) : 0, n, q, sm);
+    } else if (args.fx.load_mode == AB_MX_LOAD_GARNER) {
+        const AbMxFused &fx = args.fx;
+        const int k = fx.gar_k;
+        const int64_t *src = fx.src + blockIdx.x * fx.src_ustride;
+        uint32_t qmod[AB_MX_MAX_DROP];                 // q_i mod q of this CTA
+#pragma unroll
+        for (int i = 0; i < AB_MX_MAX_DROP; ++i) qmod[i] = i < k ? fx.gar_q[i] % q : 0u;
+        const uint64_t mu = ~0ull / q;                 // Barrett constant of this CTA's modulus (floor((2^64 - 1) / q) = floor(2^64 / q), q odd > 1)
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            uint32_t v[AB_MX_MAX_DROP];
+            int32_t r[AB_MX_MAX_DROP];
+#pragma unroll
+            for (int i = 0; i < AB_MX_MAX_DROP; ++i) v[i] = i < k ? (uint32_t)__ldcs(src - (int64_t)i * n + j) : 0u;   // drop order: last limb first
+#pragma unroll
+            for (int i = 0; i < AB_MX_MAX_DROP; ++i) {
+                if (i >= k) break;
+                r[i] = ab_center(v[i], fx.gar_q[i]);
+#pragma unroll
+                for (int t = i + 1; t < AB_MX_MAX_DROP; ++t) {
+                    if (t >= k) break;
+                    const uint32_t qt = fx.gar_q[t];
+                    v[t] = ab_shoup(ab_submod(v[t], mx_reduce_signed(r[i], qt), qt), fx.gar_inv[i][t], fx.gar_inv_s[i][t], qt);
+                }
+            }
+            uint32_t acc = mx_reduce_signed(r[k - 1], q);
+            for (int i = k - 2; i >= 0; --i) acc = ab_addmod(ab_mulmod(acc, qmod[i], q, mu), mx_reduce_signed(r[i], q), q);
+            sm[j] = acc;
+        }
     } else if (args.fx.load_mode == AB_MX_LOAD_SRC) {
         // out of place: read the transform from another planar buffer (e.g. c2 of a degree-2 ciphertext)
         const int4 *src = reinterpret_cast<const int4 *>(args.fx.src + blockIdx.x * args.fx.src_ustride + (int64_t)(args.fx.src_limb0 + limb) * n);

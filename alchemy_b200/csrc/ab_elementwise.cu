@@ -426,8 +426,8 @@ void ab_launch_sub_scale(const ab_plan *p, int64_t *out, int64_t out_bstride, co
 
 // SymmSHE (*): out3[b] = g * (a0 b0, a0 b1 + a1 b0, a1 b1), CRT basis
 struct CmArgs {
-    struct { uint32_t q, pad; uint64_t mu; const uint2 *g; } limb[AB_MAX_LIMBS];
-    int32_t nlimbs;
+    struct { uint32_t q, up, up_s, pad; uint64_t mu; const uint2 *g; } limb[AB_MAX_LIMBS];
+    int32_t nlimbs, nout;      // nout > nlimbs: the product is written at nout limbs, scaled by the appended moduli (rescale up fused)
     int64_t n, batch;
 };
 __global__ void __launch_bounds__(256) k_ct_mul(const CmArgs a, int64_t *__restrict__ out, const int64_t *__restrict__ x, const int64_t *__restrict__ y) {
@@ -443,16 +443,38 @@ __global__ void __launch_bounds__(256) k_ct_mul(const CmArgs a, int64_t *__restr
         const uint2 g = __ldg(a.limb[l].g + j);
         const uint32_t c0 = ab_mulmod(a0, b0, q, mu), c2 = ab_mulmod(a1, b1, q, mu);
         const uint32_t c1 = ab_addmod(ab_mulmod(a0, b1, q, mu), ab_mulmod(a1, b0, q, mu), q);
-        out[(b * 3 + 0) * per + r] = (int64_t)ab_shoup(c0, g, q);
-        out[(b * 3 + 1) * per + r] = (int64_t)ab_shoup(c1, g, q);
-        out[(b * 3 + 2) * per + r] = (int64_t)ab_shoup(c2, g, q);
+        uint32_t o0 = ab_shoup(c0, g, q), o1 = ab_shoup(c1, g, q), o2 = ab_shoup(c2, g, q);
+        if (a.nout > a.nlimbs) {
+            o0 = ab_shoup(o0, a.limb[l].up, a.limb[l].up_s, q);
+            o1 = ab_shoup(o1, a.limb[l].up, a.limb[l].up_s, q);
+            o2 = ab_shoup(o2, a.limb[l].up, a.limb[l].up_s, q);
+        }
+        const int64_t pero = (int64_t)a.nout * a.n;
+        out[(b * 3 + 0) * pero + r] = (int64_t)o0;
+        out[(b * 3 + 1) * pero + r] = (int64_t)o1;
+        out[(b * 3 + 2) * pero + r] = (int64_t)o2;
+    }
+    if (a.nout > a.nlimbs) {       // appended limbs are zero
+        const int64_t pero = (int64_t)a.nout * a.n, tail = pero - per, ztotal = a.batch * 3 * tail;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ztotal; i += (int64_t)gridDim.x * blockDim.x)
+            out[(i / tail) * pero + per + i % tail] = 0;
     }
 }
 void ab_launch_ct_mul(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, cudaStream_t st) {
+    ab_launch_ct_mul_up(p, out3, a2, b2, batch, nlimbs, nlimbs, st);
+}
+// (*) written directly at nout >= nlimbs limbs: modSwitch up (multiply by the appended moduli, zero limbs) in the same pass
+void ab_launch_ct_mul_up(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, int32_t nout, cudaStream_t st) {
     if (batch == 0) return;
     CmArgs a{};
-    a.nlimbs = nlimbs; a.n = p->n; a.batch = batch;
-    for (int l = 0; l < nlimbs; ++l) { a.limb[l].q = p->limb[l].q; a.limb[l].mu = p->limb[l].mu; a.limb[l].g = reinterpret_cast<const uint2 *>(p->limb[l].g_crt); }
+    a.nlimbs = nlimbs; a.nout = nout; a.n = p->n; a.batch = batch;
+    for (int l = 0; l < nlimbs; ++l) {
+        a.limb[l].q = p->limb[l].q; a.limb[l].mu = p->limb[l].mu; a.limb[l].g = reinterpret_cast<const uint2 *>(p->limb[l].g_crt);
+        const uint64_t q = (uint64_t)p->q[l];
+        uint64_t up = 1;
+        for (int k = nlimbs; k < nout; ++k) up = abh::mulmod(up, (uint64_t)p->q[k] % q, q);
+        a.limb[l].up = (uint32_t)up; a.limb[l].up_s = abh::shoup(up, q);
+    }
     k_ct_mul<<<grid_for(batch * nlimbs * p->n, 256, p->sm_count), 256, 0, st>>>(a, out3, a2, b2);
     ab_count_launch();
     ab_check_launch("ct_mul");

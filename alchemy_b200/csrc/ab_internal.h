@@ -153,7 +153,8 @@ struct AbMxStep {
 #define AB_MX_MAX_STEPS 24
 
 // fused load / store of the mixed-radix CRT kernel (key switch, tunnel, modSwitch; ab_she.cpp)
-enum { AB_MX_LOAD_PLAIN = 0, AB_MX_LOAD_DIGITS = 1, AB_MX_LOAD_SRC = 2 };
+enum { AB_MX_LOAD_PLAIN = 0, AB_MX_LOAD_DIGITS = 1, AB_MX_LOAD_SRC = 2, AB_MX_LOAD_GARNER = 3 };
+#define AB_MX_MAX_DROP 4
 enum { AB_MX_STORE_PLAIN = 0, AB_MX_STORE_SUBSCALE = 1 };
 #define AB_MX_MAX_DIGITS 64
 struct AbMxFused {
@@ -172,6 +173,14 @@ struct AbMxFused {
     // Lol's iterated divModCent are the ordinary base-b digits of c + H shifted by hb:
     //   d_i = (floor((c + H) / b^i) mod b) - hb  (i < k-1),   d_(k-1) = floor((c + H) / b^(k-1))
     struct { uint32_t q_src, pw, H; int16_t limb, last; } dig[AB_MX_MAX_DIGITS];
+    // AB_MX_LOAD_GARNER: several RNS limbs dropped in ONE rescale (modSwitch from L to L - gar_k limbs).  src holds the
+    // dropped limbs in the powerful basis, [unit][gar_k][n] in DROP order (i = 0 is the last limb).  Per coefficient the
+    // centred digits of the sequential drops are r_0 = centre(v_0), v_t <- (v_t - r_0) q_0^-1 mod q_t, r_1 = centre(v_1), ...
+    // and the value to subtract in every kept limb is x = r_0 + q_0 (r_1 + q_1 (...)) mod q  (Horner): dropping limbs one at a
+    // time gives the same integers, because q_0 r_1 + r_0 is again a centred remainder (|.| <= (q_0 q_1 - 1) / 2).
+    int32_t gar_k, pad1;
+    uint32_t gar_q[AB_MX_MAX_DROP];
+    uint32_t gar_inv[AB_MX_MAX_DROP][AB_MX_MAX_DROP], gar_inv_s[AB_MX_MAX_DROP][AB_MX_MAX_DROP];   // [i][t] = q_i^-1 mod q_t, t > i
     // AB_MX_STORE_SUBSCALE: y = (sub_in - x) * scale[limb]
     const int64_t *sub_in;
     int64_t sub_ustride;

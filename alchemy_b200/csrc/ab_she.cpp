@@ -88,6 +88,44 @@ static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, i
         int64_t cur_stride = from * n;
         for (int32_t L = from; L > to; --L) {
             const int32_t d = L - 1;
+            static const bool no_multi = getenv("AB_NO_MULTIDROP") && atoi(getenv("AB_NO_MULTIDROP")) != 0;      // A/B measurements only
+            if (!no_multi && L - to >= 2 && fused_ok(p, L, cur, work) && ((uintptr_t)out & 15) == 0 && ((cur_stride * 8) % 16) == 0) {
+                // drop k = min(L - to, 4) limbs in ONE rescale: crtInv of the k dropped limbs in one launch, then one kernel per
+                // batch that rebuilds, per coefficient, the centred digits of the sequential drops (Garner), reduces
+                // x = r_0 + q_0 (r_1 + ...) into each kept modulus, transforms it and applies (in - x) (q_0 q_1 ...)^-1:
+                // k inverse + (L - k) forward transforms per polynomial instead of k + (L-1) + (L-2) + ...
+                const int32_t k = std::min<int32_t>(L - to, AB_MX_MAX_DROP), keep = L - k;
+                AbMxFused fi{};
+                fi.load_mode = AB_MX_LOAD_SRC; fi.src = cur; fi.src_ustride = cur_stride; fi.src_limb0 = keep;
+                ab_launch_crt_mixed_fused(p, AbView{dropped, R, keep, k, AB_LAYOUT_PLANAR}, true, &fi, st);    // [R][k][n], ascending limbs
+                AbMxFused fx{};
+                fx.load_mode = AB_MX_LOAD_GARNER; fx.store_mode = AB_MX_STORE_SUBSCALE;
+                // drop order: i = 0 is limb L-1; the kernel reads src + i*n, so point it at the last limb and step backwards
+                fx.src = dropped + (int64_t)(k - 1) * n; fx.src_ustride = (int64_t)k * n; fx.gar_k = k;
+                for (int i = 0; i < k; ++i) {
+                    const uint64_t qi = (uint64_t)p->q[L - 1 - i];
+                    fx.gar_q[i] = (uint32_t)qi;
+                    for (int t2 = i + 1; t2 < k; ++t2) {
+                        const uint64_t qt = (uint64_t)p->q[L - 1 - t2];
+                        const uint64_t inv = abh::invmod(qi % qt, qt);
+                        fx.gar_inv[i][t2] = (uint32_t)inv; fx.gar_inv_s[i][t2] = abh::shoup(inv, qt);
+                    }
+                }
+                fx.sub_in = cur; fx.sub_ustride = cur_stride;
+                for (int kk = 0; kk < keep; ++kk) {
+                    const uint64_t qk = (uint64_t)p->q[kk];
+                    uint64_t prod = 1;
+                    for (int i = 0; i < k; ++i) prod = abh::mulmod(prod, (uint64_t)p->q[L - 1 - i] % qk, qk);
+                    const uint64_t inv = abh::invmod(prod, qk);
+                    fx.scale[kk] = (uint32_t)inv; fx.scale_s[kk] = abh::shoup(inv, qk);
+                }
+                int64_t *dst_buf = (keep == to) ? out + r0 * to * n : ((cur == ping) ? pong : ping);
+                ab_launch_crt_mixed_fused(p, AbView{dst_buf, R, 0, keep, AB_LAYOUT_PLANAR}, false, &fx, st);
+                cur = dst_buf;
+                cur_stride = (int64_t)keep * n;
+                L = keep + 1;          // the loop's --L lands on `keep`
+                continue;
+            }
             if (fused_ok(p, L, cur, work) && ((uintptr_t)out & 15) == 0 && ((cur_stride * 8) % 16) == 0) {
                 // two launches per dropped limb: crtInv of that limb (out of place), then one kernel that lifts it,
                 // reduces it into each kept modulus, transforms it and applies (in - x) * q_d^-1 on the way out
@@ -406,8 +444,12 @@ extern "C" int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int6
         int64_t *c3 = (int64_t *)work, *c3h = c3 + batch * 3 * lin * n, *c2h = c3h + batch * 3 * lh * n;
         void *w = c2h + batch * 2 * lh * n;
         auto must = [](int rc) { if (rc != AB_OK) throw ab_error{rc, ab_last_error()}; };
-        must(ab_ct_mul_dev(p, c3, a2, b2, batch, lin, stream));
-        must(ab_mod_switch_dev(p, c3h, c3, batch, 3, lin, lh, w, stream));
+        if (lh >= lin) {
+            ab_launch_ct_mul_up(p, c3h, a2, b2, batch, lin, lh, (cudaStream_t)stream);      // product and scale-up in one pass
+        } else {
+            must(ab_ct_mul_dev(p, c3, a2, b2, batch, lin, stream));
+            must(ab_mod_switch_dev(p, c3h, c3, batch, 3, lin, lh, w, stream));
+        }
         must(ab_key_switch_quad_dev(p, c2h, c3h, hint, batch, lh, base, w, stream));
         must(ab_mod_switch_dev(p, out2, c2h, batch, 2, lh, lout, w, stream));
     });

@@ -98,7 +98,10 @@ def test_mul_keyswitch_pipeline(m, moduli, lin, lh, lout, base):
 
 
 @pytest.mark.parametrize("m,moduli,frm,to", [(512, ARITH_Q, 3, 1), (512, ARITH_Q, 1, 3), (20475, RLWR_Q, 6, 2), (20475, RLWR_Q, 5, 5),
-                                              (45, [181, 541, 631], 3, 2), (11648, TUNNEL_Q, 2, 1)])
+                                              (45, [181, 541, 631], 3, 2), (11648, TUNNEL_Q, 2, 1),
+                                              # several limbs dropped in one rescale (Garner digits in the load phase of the transform)
+                                              (20475, RLWR_Q, 5, 3), (20475, RLWR_Q, 6, 1), (45, [181, 541, 631], 3, 1), (43680, RLWR_Q, 6, 3),
+                                              (11648, TUNNEL_Q, 5, 2), (36, [37, 73, 109], 3, 1)])
 def test_mod_switch(m, moduli, frm, to):
     import alchemy_b200 as ab
     from alchemy_b200 import she
