@@ -12,7 +12,10 @@
 #include "ab_internal.h"
 #include "ab_kernels.h"
 
-static const int64_t kChunkBytes = 512ll << 20;   // scratch per chunk: large enough that every launch fills the 148 SMs
+// scratch per chunk: every launch of a chunk should be many waves of CTAs deep (one CTA of the fused inner product runs for
+// milliseconds, so a chunk of less than a few waves leaves SMs idle in its last wave)
+static const int64_t kChunkBytes = 2048ll << 20;
+static const int64_t kMacChunkBytes = 4096ll << 20;   // the fused paths keep only O(1) polynomials per ciphertext in scratch
 
 static int64_t chunk_of(int64_t batch, int64_t bytes_per_item) {
     int64_t c = kChunkBytes / std::max<int64_t>(1, bytes_per_item);
@@ -178,11 +181,16 @@ extern "C" int ab_mod_switch_dev(const ab_plan *p, int64_t *out, const int64_t *
 
 // ------------------------------------------------------------------------------------ keySwitchQuadCirc
 static int64_t ks_item_words(const ab_plan *p, int32_t nlimbs, int32_t ndig) { return p->n * nlimbs * (1 + (int64_t)ndig); }
+static int64_t ks_mac_chunk(const ab_plan *p, int64_t batch, int32_t nlimbs) {
+    return std::min<int64_t>(batch, std::max<int64_t>(1, kMacChunkBytes / (3 * (int64_t)nlimbs * p->n * 8)));
+}
 extern "C" int64_t ab_key_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t nlimbs, int32_t base) {
     const int32_t nd = ab_gadget_len(p, nlimbs, base);
     if (nd < 0 || batch < 0) return -1;
     const int64_t w = ks_item_words(p, nlimbs, nd);
-    return chunk_of(batch, w * 8) * w * 8 + (int64_t)nd * 2 * nlimbs * p->n * 8;     // + the prepared hint
+    const int64_t generic = chunk_of(batch, w * 8) * w * 8;
+    const int64_t fused = ks_mac_chunk(p, batch, nlimbs) * 3 * nlimbs * p->n * 8;          // c2, running sums, centred source
+    return std::max(generic, fused) + (int64_t)nd * 2 * nlimbs * p->n * 8;     // + the prepared hint
 }
 extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int64_t *in3, const int64_t *hint, int64_t batch, int32_t nlimbs,
                                       int32_t base, void *work, void *stream) {
@@ -200,7 +208,7 @@ extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int
             // two launches per chunk: crtInv of c2 straight out of the input, then the fused gadget inner product
             // (digit extraction, forward CRT and multiply-accumulate on chip; ab_crt_mixed.cu k_crt_mixed_mac)
             ab_launch_hint_prep2(p, hm, hint, nd, nlimbs, st);
-            const int64_t chunk2 = std::min(batch, std::max<int64_t>(1, chunk * (1 + (int64_t)nd) / 3));     // scratch: c2, running sums, centred source
+            const int64_t chunk2 = ks_mac_chunk(p, batch, nlimbs);     // scratch: c2, running sums, centred source
             for (int64_t b0 = 0; b0 < batch; b0 += chunk2) {
                 const int64_t B = std::min(chunk2, batch - b0);
                 int64_t *c2 = work2, *accs = c2 + B * per, *tb = accs + B * per;
@@ -214,7 +222,7 @@ extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int
                 fx.src = c2; fx.src_ustride = per; fx.n_src = (int32_t)n; fx.gK = 1;
                 if (base == 0) { fx.triv_src = in + 2 * per; fx.triv_ustride = 3 * per; }
                 AbMxMac mac{};
-                mac.hm = hm; mac.K = 1; mac.add = in; mac.add_ustride = 3 * per; mac.acc = accs; mac.tbuf = (1 + (int64_t)nd >= 3) ? tb : nullptr;
+                mac.hm = hm; mac.K = 1; mac.add = in; mac.add_ustride = 3 * per; mac.acc = accs; mac.tbuf = tb;
                 mac.out = out2 + b0 * 2 * per; mac.out_ustride = 2 * per;
                 ab_launch_crt_mixed_mac(p, B, nlimbs, fx, mac, st);
             }
@@ -315,12 +323,19 @@ extern "C" void ab_tunnel_destroy(ab_tunnel *t) {
 static int64_t tn_item_words(const ab_tunnel *t, int32_t nlimbs, int32_t nd) {
     return 3 * (int64_t)nlimbs * t->r->n + (int64_t)nlimbs * t->s->n * (t->K * (2 + nd) + 1);
 }
+// fused path: crtInv'd input 2 L n_r, decoding-basis c0 L n_r, c0 parts K L n_s, evalLin result, running sums, centred source
+static int64_t tn_mac_words(const ab_tunnel *t, int32_t nlimbs) { return 3 * (int64_t)nlimbs * t->r->n + (t->K + 3) * (int64_t)nlimbs * t->s->n; }
+static int64_t tn_mac_chunk(const ab_tunnel *t, int64_t batch, int32_t nlimbs) {
+    return std::min<int64_t>(batch, std::max<int64_t>(1, kMacChunkBytes / (tn_mac_words(t, nlimbs) * 8)));
+}
 extern "C" int64_t ab_tunnel_work_bytes(const ab_tunnel *t, int64_t batch, int32_t nlimbs, int32_t base) {
     if (!t || batch < 0) return -1;
     const int32_t nd = ab_gadget_len(t->s, nlimbs, base);
     if (nd < 0) return -1;
     const int64_t w = tn_item_words(t, nlimbs, nd);
-    return chunk_of(batch, w * 8) * w * 8 + t->K * (int64_t)nd * 2 * nlimbs * t->s->n * 8;      // + the prepared hint
+    const int64_t generic = chunk_of(batch, w * 8) * w * 8;
+    const int64_t fused = tn_mac_chunk(t, batch, nlimbs) * tn_mac_words(t, nlimbs) * 8;
+    return std::max(generic, fused) + t->K * (int64_t)nd * 2 * nlimbs * t->s->n * 8;      // + the prepared hint
 }
 
 extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t *in2_r, const int64_t *flin, const int64_t *hint, int64_t batch,
@@ -340,9 +355,7 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
         int64_t *work2 = hm + K * (int64_t)nd * 2 * per_s;
         if (batch > 0 && mac_ok(ps, nlimbs, out2_s, work) && ((per_r * 8) % 16) == 0) {
             ab_launch_hint_prep2(ps, hm, hint, K * (int64_t)nd, nlimbs, st);
-            // scratch per ciphertext without the digit buffers: 3 L n_r + (K + 3) L n_s words
-            const int64_t w_old = tn_item_words(t, nlimbs, nd), w_new = 3 * per_r + (K + 3) * per_s;
-            const int64_t chunk2 = std::min(batch, std::max<int64_t>(1, chunk * w_old / w_new));
+            const int64_t chunk2 = tn_mac_chunk(t, batch, nlimbs);
             for (int64_t b0 = 0; b0 < batch; b0 += chunk2) {
                 const int64_t B = std::min(chunk2, batch - b0);
                 int64_t *cin = work2;                    // [B][2][L][n_r]
