@@ -367,6 +367,25 @@ __device__ __forceinline__ void mx_digit_from_t(const AbMxFused &fx, int d, int 
     }
 }
 
+// L (inverse = false: running sums) or L^-1 (differences) along the p-1 axis of every odd prime, on the residues in
+// shared memory; one vector of d = p-1 strided residues per work item, a barrier after every axis
+__device__ __forceinline__ void mx_l_pass(uint32_t *sm, int n, const AbMxFused &fx, uint32_t q, bool inverse) {
+    for (int a = 0; a < fx.n_odd; ++a) {
+        const int d = fx.odd[a].d, rts = fx.odd[a].rts, nvec = n / d;
+        for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+            const int t = v / rts, r = v - t * rts;
+            uint32_t *e = sm + t * d * rts + r;
+            uint32_t run = 0;
+            for (int k = 0; k < d; ++k) {
+                const uint32_t c = e[k * rts];
+                if (!inverse) { run = ab_addmod(run, c, q); e[k * rts] = run; }
+                else { e[k * rts] = ab_submod(c, run, q); run = c; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <bool INV>
 __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_constant__ MxArgs args, int64_t *__restrict__ y) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -446,8 +465,10 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
     }
     (void)skip_program;
     __syncthreads();
+    if (!INV && args.fx.pre_l) mx_l_pass(sm, n, args.fx, q, false);
     if (wide) run_program<INV, true>(args, sm, tab, q, qinv_neg);
     else run_program<INV, false>(args, sm, tab, q, qinv_neg);
+    if (INV && args.fx.post_linv) mx_l_pass(sm, n, args.fx, q, true);
     if (args.fx.store_mode == AB_MX_STORE_SUBSCALE) {
         // RNS rescale epilogue: out = (in - x) * q_drop^-1 mod q   (x = CRT of the lifted dropped limb)
         const int64_t *in = args.fx.sub_in + blockIdx.x * args.fx.sub_ustride + (int64_t)limb * n;
@@ -667,6 +688,11 @@ void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, 
     if (v.batch == 0) return;
     MxArgs args{};
     if (fx) args.fx = *fx;
+    if (args.fx.pre_l || args.fx.post_linv) {
+        args.fx.n_odd = 0;
+        for (const AbAxis &ax : p->axes)
+            if (ax.p != 2) { args.fx.odd[args.fx.n_odd].d = ax.p - 1; args.fx.odd[args.fx.n_odd].rts = (int32_t)ax.rts; ++args.fx.n_odd; }
+    }
     const auto &steps = inverse ? p->mx_inv : p->mx_fwd;
     args.nsteps = (int32_t)steps.size();
     for (size_t i = 0; i < steps.size(); ++i) args.steps[i] = steps[i];
@@ -678,6 +704,7 @@ void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, 
     args.batch = v.batch;
     if (v.layout == AB_LAYOUT_PLANAR) { args.estride = 1; args.lstride = p->n; args.bstride = p->n * v.nlimbs; }
     else { args.estride = v.nlimbs; args.lstride = 1; args.bstride = p->n * v.nlimbs; }
+    if (args.fx.dst_ustride) args.bstride = args.fx.dst_ustride;
     for (int l = 0; l < v.nlimbs; ++l) {
         const AbLimbDev &ld = p->limb[v.limb0 + l];
         args.limb[l].q = ld.q;

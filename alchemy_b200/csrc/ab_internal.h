@@ -181,6 +181,12 @@ struct AbMxFused {
     int32_t gar_k, pad1;
     uint32_t gar_q[AB_MX_MAX_DROP];
     uint32_t gar_inv[AB_MX_MAX_DROP][AB_MX_MAX_DROP], gar_inv_s[AB_MX_MAX_DROP][AB_MX_MAX_DROP];   // [i][t] = q_i^-1 mod q_t, t > i
+    // Dec <-> Pow folded into the transform: pre_l applies L (decoding -> powerful) to the loaded residues before a forward
+    // program, post_linv applies L^-1 after an inverse program (Lol `l` / `lInv`: running sums / differences along the
+    // p-1 axis of every odd prime); the axes are filled in by the launcher
+    int32_t pre_l, post_linv, n_odd, pad2;
+    int64_t dst_ustride;             // 0: units are contiguous in the destination; else int64 words between consecutive units
+    struct { int32_t d, rts; } odd[AB_MAX_AXES];
     // AB_MX_STORE_SUBSCALE: y = (sub_in - x) * scale[limb]
     const int64_t *sub_in;
     int64_t sub_ustride;

@@ -364,13 +364,31 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                 int64_t *lin = p0 + B * K * per_s;       // [B][L][n_s]
                 int64_t *accs = lin + B * per_s;         // [B][L][n_s] running sums of the fused inner product
                 int64_t *tb = accs + B * per_s;          // [B][L][n_s] centred source + H of the current (k, source limb)
-                ab_launch_copy_rows(cin, 2 * per_r, in2_r + b0 * 2 * per_r, 2 * per_r, 2 * per_r, B, st);
-                ab_crt_dispatch(pr, AbView{cin, B * 2, 0, nlimbs, AB_LAYOUT_PLANAR}, true, st);
-                ab_launch_copy_rows(c0d, per_r, cin, 2 * per_r, per_r, B, st);
-                ab_launch_prime_op(pr, AB_PR_LINV, AbView{c0d, B, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
-                ab_launch_tunnel_gather(ps, p0, c0d, per_r, nr, t->d_dec, t->d_dec_sgn, B, K, nlimbs, st);
-                ab_launch_prime_op(ps, AB_PR_L, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
-                ab_crt_dispatch(ps, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
+                const int64_t *inb = in2_r + b0 * 2 * per_r;
+                if (fused_ok(pr, nlimbs, inb, cin) && ((2 * per_r * 8) % 16) == 0) {
+                    // c0 straight to the decoding basis (crtInv with L^-1 folded in), c1 to the powerful basis: two out-of-place
+                    // launches, no copies, no separate L / L^-1 passes; L is folded into the load phase of the forward CRT of the parts
+                    AbMxFused f0{};
+                    f0.load_mode = AB_MX_LOAD_SRC; f0.src = inb; f0.src_ustride = 2 * per_r; f0.src_limb0 = 0; f0.post_linv = 1;
+                    ab_launch_crt_mixed_fused(pr, AbView{c0d, B, 0, nlimbs, AB_LAYOUT_PLANAR}, true, &f0, st);
+                    AbMxFused f1{};
+                    f1.load_mode = AB_MX_LOAD_SRC; f1.src = inb + per_r; f1.src_ustride = 2 * per_r; f1.src_limb0 = 0;
+                    // c1 lands in the second half of every cin row so that the digit source below keeps its layout
+                    f1.dst_ustride = 2 * per_r;
+                    ab_launch_crt_mixed_fused(pr, AbView{cin + per_r, B, 0, nlimbs, AB_LAYOUT_PLANAR}, true, &f1, st);
+                    ab_launch_tunnel_gather(ps, p0, c0d, per_r, nr, t->d_dec, t->d_dec_sgn, B, K, nlimbs, st);
+                    AbMxFused fl{};
+                    fl.pre_l = 1;
+                    ab_launch_crt_mixed_fused(ps, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, &fl, st);
+                } else {
+                    ab_launch_copy_rows(cin, 2 * per_r, inb, 2 * per_r, 2 * per_r, B, st);
+                    ab_crt_dispatch(pr, AbView{cin, B * 2, 0, nlimbs, AB_LAYOUT_PLANAR}, true, st);
+                    ab_launch_copy_rows(c0d, per_r, cin, 2 * per_r, per_r, B, st);
+                    ab_launch_prime_op(pr, AB_PR_LINV, AbView{c0d, B, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
+                    ab_launch_tunnel_gather(ps, p0, c0d, per_r, nr, t->d_dec, t->d_dec_sgn, B, K, nlimbs, st);
+                    ab_launch_prime_op(ps, AB_PR_L, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
+                    ab_crt_dispatch(ps, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
+                }
                 ab_launch_lin_ip(ps, lin, per_s, p0, K * per_s, flin, B, nlimbs, (int32_t)K, st);
                 // c1: gather (coeffs . embed), gadget digit, reduction, forward CRT of O_s' and the inner product with
                 // the hint, all inside one kernel; the evalLin part of c0 is added on the way out
