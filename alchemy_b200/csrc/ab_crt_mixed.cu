@@ -516,20 +516,25 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
     uint32_t *sm = smem + tab_words;
     const uint32_t q = args.limb[limb].q, qinv_neg = args.limb[limb].qinv_neg;
     const AbMxFused &fx = args.fx;
-    const int64_t unit = blockIdx.x;
+    const int parts = mac.parts > 1 ? mac.parts : 1;
+    const int64_t unit = blockIdx.x / parts, slice = blockIdx.x;          // slice = unit * parts + part
+    const int part = (int)(blockIdx.x - unit * parts);
     uint2 *acc = ACC_SMEM ? reinterpret_cast<uint2 *>(sm + nb)
-                          : reinterpret_cast<uint2 *>(mac.acc) + (unit * args.nlimbs + limb) * (int64_t)n;
+                          : reinterpret_cast<uint2 *>(mac.acc) + (slice * args.nlimbs + limb) * (int64_t)n;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(args.limb[limb].tab);
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
         for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    int64_t *tbuf = (mac.tbuf && fx.gbase != 0) ? mac.tbuf + (unit * args.nlimbs + limb) * (int64_t)n : nullptr;
+    int64_t *tbuf = (mac.tbuf && fx.gbase != 0) ? mac.tbuf + (slice * args.nlimbs + limb) * (int64_t)n : nullptr;
     const uint2 *hm = reinterpret_cast<const uint2 *>(mac.hm) + (int64_t)limb * n;
     const int64_t hstride = (int64_t)args.nlimbs * n;
     bool first = true;
-    for (int k = 0; k < mac.K; ++k) {
-        for (int d = 0; d < fx.nd; ++d) {
+    const int total_digits = mac.K * fx.nd, per_part = (total_digits + parts - 1) / parts;
+    const int kd0 = part * per_part, kd1 = min(total_digits, kd0 + per_part);
+    {
+        for (int kd = kd0; kd < kd1; ++kd) {
+            const int k = kd / fx.nd, d = kd - k * fx.nd;
             const bool triv = mx_digit_is_trivial(fx, d, limb);
             if (triv) {
                 const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
@@ -539,7 +544,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
                     dst[i] = make_uint2((uint32_t)v.x, (uint32_t)v.z);
                 }
             } else if (tbuf) {
-                if (d == 0 || fx.dig[d].limb != fx.dig[d - 1].limb) {
+                if (kd == kd0 || d == 0 || fx.dig[d].limb != fx.dig[d - 1].limb) {
                     mx_gather_centered(fx, d, unit, k, n, tbuf);
                     __syncthreads();      // the digit pass reads t with a different thread-to-position map
                 }
@@ -593,7 +598,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
             __syncthreads();       // the next digit overwrites sm
         }
     }
-    {
+    if (first && !ACC_SMEM) {       // a part that received no digit (parts does not divide the digit count): its partial sum is zero
+        for (int j = threadIdx.x; j < n; j += blockDim.x) __stcg(acc + j, make_uint2(0, 0));
+    }
+    if (parts == 1) {
         const int64_t per = hstride;
         int64_t *o0 = mac.out + unit * mac.out_ustride + (int64_t)limb * n, *o1 = o0 + per;
         const int64_t *a0 = mac.add ? mac.add + unit * mac.add_ustride + (int64_t)limb * n : nullptr;
@@ -618,6 +626,29 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
     }
 }
 
+// out_c = add_c + sum over the parts of a unit of the partial sums (parts > 1 only)
+__global__ void __launch_bounds__(256) k_mac_combine(const __grid_constant__ MxArgs args, const __grid_constant__ AbMxMac mac) {
+    const int n = args.n, L = args.nlimbs, parts = mac.parts;
+    const int64_t per = (int64_t)L * n, total = args.batch * per;
+    const uint2 *acc = reinterpret_cast<const uint2 *>(mac.acc);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t unit = i / per, r = i - unit * per;
+        const uint32_t q = args.limb[(int)(r / n)].q;
+        uint32_t s0 = 0, s1 = 0;
+        for (int pt = 0; pt < parts; ++pt) {
+            const uint2 a = __ldcs(acc + (unit * parts + pt) * per + r);
+            s0 = ab_addmod(s0, a.x, q); s1 = ab_addmod(s1, a.y, q);
+        }
+        if (mac.add) {
+            s0 = ab_addmod(s0, (uint32_t)__ldcs(mac.add + unit * mac.add_ustride + r), q);
+            s1 = ab_addmod(s1, (uint32_t)__ldcs(mac.add + unit * mac.add_ustride + per + r), q);
+        }
+        if (mac.add0) s0 = ab_addmod(s0, (uint32_t)__ldcs(mac.add0 + unit * mac.add0_ustride + r), q);
+        __stcs(mac.out + unit * mac.out_ustride + r, (int64_t)s0);
+        __stcs(mac.out + unit * mac.out_ustride + per + r, (int64_t)s1);
+    }
+}
+
 bool ab_mixed_supported(const ab_plan *p, const AbView &v) {
     if (p->mx_ok.empty() || p->mx_fwd.empty() || p->mx_tab_fwd.empty()) return false;
     for (int l = 0; l < v.nlimbs; ++l)
@@ -631,13 +662,6 @@ bool ab_mixed_supported(const ab_plan *p, const AbView &v) {
 // 384 items -> 1.5 rounds at T = 256).  Model: time of one transform ~ sum over passes of rounds * work per item,
 // throughput ~ resident CTAs / time; resident CTAs from shared memory and the 64-register budget (1024 threads).
 // Measured on B200 (tools/sweep_crt.py, AB_MX_T): within 3 % of the best of {128, 160, 192, 224, 256} on every example ring.
-// CTA size: every pass hands ceil(items / T) work items to each thread and ends in a barrier, so a T that does not
-// divide the item counts leaves threads idle in the last round (n = 9216, 12-point steps, two columns per item:
-// 384 items -> 1.5 rounds at T = 256).  Model: time of one transform ~ sum over passes of rounds * work per item,
-// throughput ~ resident CTAs / time; resident CTAs from shared memory and the 64-register budget (1024 threads).
-// Measured on B200 (tools/sweep_crt.py, AB_MX_T): within 3 % of the best of {128, 160, 192, 224, 256} on every example ring.
-// fixed number of resident CTAs (the caller's shared-memory budget decides it): the T that wastes the fewest thread
-// slots over the passes, larger T on ties
 static int pick_threads_among(const std::vector<AbMxStep> &steps, int n, std::initializer_list<int> cand) {
     int best_t = *cand.begin();
     double best = 1e300;
@@ -760,9 +784,21 @@ bool ab_mixed_mac_supported(const ab_plan *p, int32_t nlimbs) {
     if (ab_pow2_supported(p) || (p->n & 1)) return false;
     return ab_mixed_supported(p, AbView{nullptr, 1, 0, nlimbs, AB_LAYOUT_INTERLEAVED});
 }
+// a CTA of the fused inner product runs for milliseconds: when the batch alone gives fewer than about four waves of CTAs, cut the
+// digit list of a unit into parts (each keeps at least eight digit transforms, so table loads and gathers stay amortised).
+// Measured on the Tunnel.hs chain: 512 ciphertexts 34.7k -> 40.2k/s; at 4096 ciphertexts splitting does not pay (left at 1 part).
+int32_t ab_mixed_mac_parts(const ab_plan *p, int64_t units, int32_t nlimbs, int32_t total_digits) {
+    static const int force = getenv("AB_MX_MAC_PARTS") ? atoi(getenv("AB_MX_MAC_PARTS")) : 0;      // experiments only
+    if (force > 0) return std::min(force, total_digits);
+    if (units <= 0) return 1;
+    const int64_t slots = (int64_t)p->sm_count * 5, want = 4 * slots;
+    int64_t parts = (want + units * nlimbs - 1) / (units * nlimbs);
+    parts = std::min<int64_t>(parts, total_digits / 8);
+    return (int32_t)std::max<int64_t>(1, parts);
+}
 int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs) {
     const int words = std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]);
-    return mac_acc_in_smem(p, words) ? 0 : units * nlimbs * p->n;      // uint2 per position = one int64 word
+    return mac_acc_in_smem(p, words) ? 0 : units * nlimbs * p->n;      // uint2 per position = one int64 word (per part when parts > 1)
 }
 
 template <bool ACC_SMEM>
@@ -785,14 +821,22 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     fill_mx_args(p, args, 0, nlimbs, false, max_words);
     args.batch = units;
     args.estride = 1; args.lstride = p->n; args.bstride = p->n * nlimbs;
-    const bool acc_smem = mac_acc_in_smem(p, std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]));
+    const int parts = mac.parts > 1 ? mac.parts : 1;
+    const bool acc_smem = parts == 1 && mac_acc_in_smem(p, std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]));
     AB_REQUIRE(acc_smem || mac.acc, AB_ERR_ARG, "fused gadget inner product: scratch missing");
     const size_t smem = mac_smem(p, max_words, acc_smem);
     static const int force_t = getenv("AB_MX_MAC_T") ? atoi(getenv("AB_MX_MAC_T")) : 0;      // experiments only
     const int T = force_t ? force_t : pick_threads(p->mx_fwd, (int)p->n, smem);
-    const dim3 grid((unsigned)units, (unsigned)nlimbs);
+    const dim3 grid((unsigned)(units * parts), (unsigned)nlimbs);
     if (acc_smem) launch_mac<true>(args, mac, grid, T, smem, st);
     else launch_mac<false>(args, mac, grid, T, smem, st);
     ab_count_launch();
     ab_check_launch("crt_mixed_mac");
+    if (parts > 1) {
+        const int64_t work = units * nlimbs * p->n;
+        const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)p->sm_count * 16));
+        k_mac_combine<<<g, 256, 0, st>>>(args, mac);
+        ab_count_launch();
+        ab_check_launch("mac_combine");
+    }
 }

@@ -198,7 +198,9 @@ struct AbMxFused {
 // hint all happen in shared memory; only the two result polynomials leave the SM.
 struct AbMxMac {
     const void *hm;              // prepared hint [K * nd][L][n] of uint2 = (h_0 2^32 mod q, h_1 2^32 mod q)  (ab_launch_hint_prep2)
-    int32_t K, pad;              // tunnel: dimension of O_r' over O_e' (digit loop runs over K * nd); key switch: 1
+    int32_t K, parts;            // tunnel: dimension of O_r' over O_e' (digit loop runs over K * nd); key switch: 1.
+                                 // parts > 1: the digit list of a unit is cut into `parts` CTAs (more, shorter CTAs: fuller
+                                 // last wave); partial sums stay in `acc` [unit][part][L][n] and k_mac_combine adds them up
     const int64_t *add;          // optional [unit][2][L][n] added to both components (key switch: c0, c1)
     int64_t add_ustride;
     const int64_t *add0;         // optional [unit][L][n] added to component 0 (tunnel: the evalLin part)
@@ -277,6 +279,7 @@ void ab_launch_mulks_pow2(const ab_plan *p, int64_t *out2, const int64_t *a2, co
                           int32_t lin, int32_t lh, int32_t lout, cudaStream_t st);
 bool ab_mixed_mac_supported(const ab_plan *p, int32_t nlimbs);
 int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs);
+int32_t ab_mixed_mac_parts(const ab_plan *p, int64_t units, int32_t nlimbs, int32_t total_digits);   // how many CTAs per unit pay off
 void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, const AbMxFused &fx, const AbMxMac &mac, cudaStream_t st);
 
 enum { AB_EW_MUL = 0, AB_EW_ADD = 1, AB_EW_SUB = 2, AB_EW_NEG = 3, AB_EW_SCALAR = 4, AB_EW_GCRT = 5, AB_EW_GINVCRT = 6 };

@@ -324,9 +324,11 @@ static int64_t tn_item_words(const ab_tunnel *t, int32_t nlimbs, int32_t nd) {
     return 3 * (int64_t)nlimbs * t->r->n + (int64_t)nlimbs * t->s->n * (t->K * (2 + nd) + 1);
 }
 // fused path: crtInv'd input 2 L n_r, decoding-basis c0 L n_r, c0 parts K L n_s, evalLin result, running sums, centred source
-static int64_t tn_mac_words(const ab_tunnel *t, int32_t nlimbs) { return 3 * (int64_t)nlimbs * t->r->n + (t->K + 3) * (int64_t)nlimbs * t->s->n; }
-static int64_t tn_mac_chunk(const ab_tunnel *t, int64_t batch, int32_t nlimbs) {
-    return std::min<int64_t>(batch, std::max<int64_t>(1, kMacChunkBytes / (tn_mac_words(t, nlimbs) * 8)));
+static int64_t tn_mac_words(const ab_tunnel *t, int32_t nlimbs, int32_t parts) {
+    return 3 * (int64_t)nlimbs * t->r->n + (t->K + 1 + 2 * (int64_t)parts) * (int64_t)nlimbs * t->s->n;
+}
+static int64_t tn_mac_chunk(const ab_tunnel *t, int64_t batch, int32_t nlimbs, int32_t parts) {
+    return std::min<int64_t>(batch, std::max<int64_t>(1, kMacChunkBytes / (tn_mac_words(t, nlimbs, parts) * 8)));
 }
 extern "C" int64_t ab_tunnel_work_bytes(const ab_tunnel *t, int64_t batch, int32_t nlimbs, int32_t base) {
     if (!t || batch < 0) return -1;
@@ -334,7 +336,8 @@ extern "C" int64_t ab_tunnel_work_bytes(const ab_tunnel *t, int64_t batch, int32
     if (nd < 0) return -1;
     const int64_t w = tn_item_words(t, nlimbs, nd);
     const int64_t generic = chunk_of(batch, w * 8) * w * 8;
-    const int64_t fused = tn_mac_chunk(t, batch, nlimbs) * tn_mac_words(t, nlimbs) * 8;
+    const int32_t parts = ab_mixed_mac_parts(t->s, batch, nlimbs, (int32_t)(t->K * nd));
+    const int64_t fused = tn_mac_chunk(t, batch, nlimbs, parts) * tn_mac_words(t, nlimbs, parts) * 8;
     return std::max(generic, fused) + t->K * (int64_t)nd * 2 * nlimbs * t->s->n * 8;      // + the prepared hint
 }
 
@@ -355,15 +358,16 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
         int64_t *work2 = hm + K * (int64_t)nd * 2 * per_s;
         if (batch > 0 && mac_ok(ps, nlimbs, out2_s, work) && ((per_r * 8) % 16) == 0) {
             ab_launch_hint_prep2(ps, hm, hint, K * (int64_t)nd, nlimbs, st);
-            const int64_t chunk2 = tn_mac_chunk(t, batch, nlimbs);
+            const int32_t parts = ab_mixed_mac_parts(ps, batch, nlimbs, (int32_t)(K * nd));
+            const int64_t chunk2 = tn_mac_chunk(t, batch, nlimbs, parts);
             for (int64_t b0 = 0; b0 < batch; b0 += chunk2) {
                 const int64_t B = std::min(chunk2, batch - b0);
                 int64_t *cin = work2;                    // [B][2][L][n_r]
                 int64_t *c0d = cin + B * 2 * per_r;      // [B][L][n_r]
                 int64_t *p0 = c0d + B * per_r;           // [B][K][L][n_s]
                 int64_t *lin = p0 + B * K * per_s;       // [B][L][n_s]
-                int64_t *accs = lin + B * per_s;         // [B][L][n_s] running sums of the fused inner product
-                int64_t *tb = accs + B * per_s;          // [B][L][n_s] centred source + H of the current (k, source limb)
+                int64_t *accs = lin + B * per_s;         // [B][parts][L][n_s] running sums of the fused inner product
+                int64_t *tb = accs + B * parts * per_s;  // [B][parts][L][n_s] centred source + H of the current (k, source limb)
                 const int64_t *inb = in2_r + b0 * 2 * per_r;
                 if (fused_ok(pr, nlimbs, inb, cin) && ((2 * per_r * 8) % 16) == 0) {
                     // c0 straight to the decoding basis (crtInv with L^-1 folded in), c1 to the powerful basis: two out-of-place
@@ -397,7 +401,7 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                 fill_digits(ps, nlimbs, base, fx, false);
                 fx.src = cin + per_r; fx.src_ustride = 2 * per_r; fx.n_src = (int32_t)nr; fx.gather = t->d_pow; fx.gK = (int32_t)K;
                 AbMxMac mac{};
-                mac.hm = hm; mac.K = (int32_t)K; mac.add0 = lin; mac.add0_ustride = per_s; mac.acc = accs; mac.tbuf = tb;
+                mac.hm = hm; mac.K = (int32_t)K; mac.add0 = lin; mac.add0_ustride = per_s; mac.acc = accs; mac.tbuf = tb; mac.parts = parts;
                 mac.out = out2_s + b0 * 2 * per_s; mac.out_ustride = 2 * per_s;
                 ab_launch_crt_mixed_mac(ps, B, nlimbs, fx, mac, st);
             }
