@@ -1,0 +1,87 @@
+// ab_crt_mixed_mac.cu -- the fused gadget inner product of keySwitchQuadCirc (Eval.hs:133) and tunnel (Eval.hs:134):
+// digit extraction, forward CRT and multiply-accumulate against the prepared hint in one kernel (sm_100a).
+#define AB_MX_MAC_SMEM 0
+#include "ab_crt_mixed_mac_kernel.cuh"
+
+void ab_mx_launch_mac_smem(dim3 grid, int T, size_t smem, cudaStream_t st, const MxArgs &args, const AbMxMac &mac);   // ab_crt_mixed_mac_smem.cu
+
+// out_c = add_c + sum over the parts of a unit of the partial sums (parts > 1 only)
+__global__ void __launch_bounds__(256) k_mac_combine(const __grid_constant__ MxArgs args, const __grid_constant__ AbMxMac mac) {
+    const int n = args.n, L = args.nlimbs, parts = mac.parts;
+    const int64_t per = (int64_t)L * n, total = args.batch * per;
+    const uint2 *acc = reinterpret_cast<const uint2 *>(mac.acc);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t unit = i / per, r = i - unit * per;
+        const uint32_t q = args.limb[(int)(r / n)].q;
+        uint32_t s0 = 0, s1 = 0;
+        for (int pt = 0; pt < parts; ++pt) {
+            const uint2 a = __ldcs(acc + (unit * parts + pt) * per + r);
+            s0 = ab_addmod(s0, a.x, q); s1 = ab_addmod(s1, a.y, q);
+        }
+        if (mac.add) {
+            s0 = ab_addmod(s0, (uint32_t)__ldcs(mac.add + unit * mac.add_ustride + r), q);
+            s1 = ab_addmod(s1, (uint32_t)__ldcs(mac.add + unit * mac.add_ustride + per + r), q);
+        }
+        if (mac.add0) s0 = ab_addmod(s0, (uint32_t)__ldcs(mac.add0 + unit * mac.add0_ustride + r), q);
+        __stcs(mac.out + unit * mac.out_ustride + r, (int64_t)s0);
+        __stcs(mac.out + unit * mac.out_ustride + per + r, (int64_t)s1);
+    }
+}
+
+static size_t mac_smem(const ab_plan *p, int max_words, bool acc_smem) {
+    const size_t nb = ((size_t)p->n + 3) & ~(size_t)3;
+    return ((size_t)max_words + nb + (acc_smem ? 2 * (size_t)p->n : 0)) * sizeof(uint32_t);
+}
+// the running sums ride in shared memory only where four CTAs still fit an SM; otherwise in the caller's scratch
+static bool mac_acc_in_smem(const ab_plan *p, int max_words) { return 4 * (mac_smem(p, max_words, true) + 1024) <= 228 * 1024; }
+bool ab_mixed_mac_supported(const ab_plan *p, int32_t nlimbs) {
+    if (ab_pow2_supported(p) || (p->n & 1)) return false;
+    return ab_mixed_supported(p, AbView{nullptr, 1, 0, nlimbs, AB_LAYOUT_INTERLEAVED});
+}
+// a CTA of the fused inner product runs for milliseconds: when the batch alone gives fewer than about four waves of CTAs, cut the
+// digit list of a unit into parts (each keeps at least eight digit transforms, so table loads and gathers stay amortised).
+// Measured on the Tunnel.hs chain: 512 ciphertexts 34.7k -> 40.2k/s; at 4096 ciphertexts splitting does not pay (left at 1 part).
+int32_t ab_mixed_mac_parts(const ab_plan *p, int64_t units, int32_t nlimbs, int32_t total_digits) {
+    static const int force = getenv("AB_MX_MAC_PARTS") ? atoi(getenv("AB_MX_MAC_PARTS")) : 0;      // experiments only
+    if (force > 0) return std::min(force, total_digits);
+    if (units <= 0) return 1;
+    const int64_t slots = (int64_t)p->sm_count * 5, want = 4 * slots;
+    int64_t parts = (want + units * nlimbs - 1) / (units * nlimbs);
+    parts = std::min<int64_t>(parts, total_digits / 8);
+    return (int32_t)std::max<int64_t>(1, parts);
+}
+int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs) {
+    const int words = std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]);
+    return mac_acc_in_smem(p, words) ? 0 : units * nlimbs * p->n;      // uint2 per position = one int64 word (per part when parts > 1)
+}
+
+void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, const AbMxFused &fx, const AbMxMac &mac, cudaStream_t st) {
+    AB_REQUIRE(ab_mixed_mac_supported(p, nlimbs), AB_ERR_UNSUPPORTED, "fused gadget inner product: plan not supported");
+    AB_REQUIRE(fx.load_mode == AB_MX_LOAD_DIGITS && fx.nd >= 1 && mac.K >= 1 && mac.hm && mac.out, AB_ERR_ARG, "fused gadget inner product: bad arguments");
+    if (units == 0) return;
+    MxArgs args{};
+    args.fx = fx;
+    int max_words = 0;
+    fill_mx_args(p, args, 0, nlimbs, false, max_words);
+    args.batch = units;
+    args.estride = 1; args.lstride = p->n; args.bstride = p->n * nlimbs;
+    const int parts = mac.parts > 1 ? mac.parts : 1;
+    const bool acc_smem = parts == 1 && mac_acc_in_smem(p, std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]));
+    AB_REQUIRE(acc_smem || mac.acc, AB_ERR_ARG, "fused gadget inner product: scratch missing");
+    const size_t smem = mac_smem(p, max_words, acc_smem);
+    static const int force_t = getenv("AB_MX_MAC_T") ? atoi(getenv("AB_MX_MAC_T")) : 0;      // experiments only
+    const int T = force_t ? force_t : pick_threads(p->mx_fwd, (int)p->n, smem);
+    const dim3 grid((unsigned)(units * parts), (unsigned)nlimbs);
+    if (acc_smem) ab_mx_launch_mac_smem(grid, T, smem, st, args, mac);
+    else ab_mx_launch_mac_glob(grid, T, smem, st, args, mac);
+    ab_count_launch();
+    ab_check_launch("crt_mixed_mac");
+    if (parts > 1) {
+        const int64_t work = units * nlimbs * p->n;
+        const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)p->sm_count * 16));
+        k_mac_combine<<<g, 256, 0, st>>>(args, mac);
+        ab_count_launch();
+        ab_check_launch("mac_combine");
+    }
+}
+

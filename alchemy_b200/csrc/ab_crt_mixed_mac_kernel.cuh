@@ -1,0 +1,148 @@
+// ab_crt_mixed_mac_kernel.cuh -- the fused gadget inner product kernel and its launch wrapper.  Included by two translation
+// units with AB_MX_MAC_SMEM set (running sums in shared memory or in the caller's scratch), so they compile in parallel.
+#pragma once
+#include "ab_crt_mixed_dev.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Fused gadget inner product: out_c = add_c + sum_{k,d} CRT(reduce(digit_{k,d}(src))) * hint_{k,d,c},  c in {0,1}.
+// The core of keySwitchQuadCirc (Eval.hs:133) and of tunnel (Eval.hs:134).  One CTA owns (unit, limb) and keeps
+// the residues of the digit being transformed (uint32 [n]) and the two running sums (uint2 [n], fully reduced)
+// in shared memory for the whole loop: the K * nd digit transforms never touch HBM.  Per digit: load + centre +
+// digit + reduce (source and gather table from L2), the forward program, then one pass x * (h0, h1) with a
+// single-term Montgomery reduction each (T = x h 2^32 < 2^62, T + m q < 2^64 for q < 2^31).
+// ACC_SMEM = false: the running sums live in a global scratch slice owned by this CTA (thread t always touches the
+// same positions j = t, t + T, ..., so no synchronisation is needed; with one wave of CTAs resident the slices stay
+// in L2) and shared memory holds only the residues: the 4 x 256-thread residency of the plain transform is kept.
+template <int MAXT, int MINB, bool ACC_SMEM>
+__global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_constant__ MxArgs args, const __grid_constant__ AbMxMac mac) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int limb = blockIdx.y;
+    const bool wide = args.limb[limb].wide != 0;
+    const int tab_words = args.tab_words[wide ? 1 : 0];
+    const int n = args.n, nb = (n + 3) & ~3;
+    uint32_t *tab = smem;
+    uint32_t *sm = smem + tab_words;
+    const uint32_t q = args.limb[limb].q, qinv_neg = args.limb[limb].qinv_neg;
+    const AbMxFused &fx = args.fx;
+    const int parts = mac.parts > 1 ? mac.parts : 1;
+    const int64_t unit = blockIdx.x / parts, slice = blockIdx.x;          // slice = unit * parts + part
+    const int part = (int)(blockIdx.x - unit * parts);
+    uint2 *acc = ACC_SMEM ? reinterpret_cast<uint2 *>(sm + nb)
+                          : reinterpret_cast<uint2 *>(mac.acc) + (slice * args.nlimbs + limb) * (int64_t)n;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(args.limb[limb].tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(tab);
+        for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    int64_t *tbuf = (mac.tbuf && fx.gbase != 0) ? mac.tbuf + (slice * args.nlimbs + limb) * (int64_t)n : nullptr;
+    const uint2 *hm = reinterpret_cast<const uint2 *>(mac.hm) + (int64_t)limb * n;
+    const int64_t hstride = (int64_t)args.nlimbs * n;
+    bool first = true;
+    const int total_digits = mac.K * fx.nd, per_part = (total_digits + parts - 1) / parts;
+    const int kd0 = part * per_part, kd1 = min(total_digits, kd0 + per_part);
+    {
+        for (int kd = kd0; kd < kd1; ++kd) {
+            const int k = kd / fx.nd, d = kd - k * fx.nd;
+            const bool triv = mx_digit_is_trivial(fx, d, limb);
+            if (triv) {
+                const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
+                uint2 *dst = reinterpret_cast<uint2 *>(sm);
+                for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+                    const int4 v = __ldcs(src + i);
+                    dst[i] = make_uint2((uint32_t)v.x, (uint32_t)v.z);
+                }
+            } else if (tbuf) {
+                if (kd == kd0 || d == 0 || fx.dig[d].limb != fx.dig[d - 1].limb) {
+                    mx_gather_centered(fx, d, unit, k, n, tbuf);
+                    __syncthreads();      // the digit pass reads t with a different thread-to-position map
+                }
+                mx_digit_from_t(fx, d, n, q, tbuf, sm);
+            } else {
+                mx_load_digit(fx, d, unit, k, n, q, sm);
+            }
+            __syncthreads();
+            if (!triv) {
+                if (wide) run_program<false, true>(args, sm, tab, q, qinv_neg);
+                else run_program<false, false>(args, sm, tab, q, qinv_neg);
+            }
+            const uint2 *hp = hm + (int64_t)(k * fx.nd + d) * hstride;
+            auto mac1 = [&](uint32_t x, uint32_t h0, uint32_t h1, uint32_t &a0, uint32_t &a1) {
+                const uint64_t t0 = (uint64_t)x * h0, t1 = (uint64_t)x * h1;
+                const uint32_t r0 = (uint32_t)((t0 + (uint64_t)((uint32_t)t0 * qinv_neg) * q) >> 32);
+                const uint32_t r1 = (uint32_t)((t1 + (uint64_t)((uint32_t)t1 * qinv_neg) * q) >> 32);
+                a0 = ab_addmod(ab_csub(r0, q), a0, q);
+                a1 = ab_addmod(ab_csub(r1, q), a1, q);
+            };
+            // four consecutive positions per thread and step: 16-byte loads of the hint pairs, the running sums and the
+            // residues; thread t owns the same positions for every digit (the sums need no synchronisation)
+            const int T = blockDim.x, n4 = n >> 2;
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(hp);
+            uint4 *a4 = reinterpret_cast<uint4 *>(acc);
+            const uint4 *x4 = reinterpret_cast<const uint4 *>(sm);
+            for (int g = threadIdx.x; g < n4; g += T) {
+                const uint4 ha = __ldg(h4 + 2 * g), hb2 = __ldg(h4 + 2 * g + 1);
+                uint4 aa = make_uint4(0, 0, 0, 0), ab2 = aa;
+                if (!first) {
+                    if (ACC_SMEM) { aa = a4[2 * g]; ab2 = a4[2 * g + 1]; }
+                    else { aa = __ldcg(a4 + 2 * g); ab2 = __ldcg(a4 + 2 * g + 1); }
+                }
+                const uint4 x = x4[g];
+                mac1(x.x, ha.x, ha.y, aa.x, aa.y);
+                mac1(x.y, ha.z, ha.w, aa.z, aa.w);
+                mac1(x.z, hb2.x, hb2.y, ab2.x, ab2.y);
+                mac1(x.w, hb2.z, hb2.w, ab2.z, ab2.w);
+                if (ACC_SMEM) { a4[2 * g] = aa; a4[2 * g + 1] = ab2; }
+                else { __stcg(a4 + 2 * g, aa); __stcg(a4 + 2 * g + 1, ab2); }
+            }
+            for (int j = 4 * n4 + threadIdx.x; j < n; j += T) {
+                const uint2 h = __ldg(hp + j);
+                uint2 a = make_uint2(0, 0);
+                if (!first) a = ACC_SMEM ? acc[j] : __ldcg(acc + j);
+                mac1(sm[j], h.x, h.y, a.x, a.y);
+                if (ACC_SMEM) acc[j] = a;
+                else __stcg(acc + j, a);
+            }
+            first = false;
+            __syncthreads();       // the next digit overwrites sm
+        }
+    }
+    if (first && !ACC_SMEM) {       // a part that received no digit (parts does not divide the digit count): its partial sum is zero
+        for (int j = threadIdx.x; j < n; j += blockDim.x) __stcg(acc + j, make_uint2(0, 0));
+    }
+    if (parts == 1) {
+        const int64_t per = hstride;
+        int64_t *o0 = mac.out + unit * mac.out_ustride + (int64_t)limb * n, *o1 = o0 + per;
+        const int64_t *a0 = mac.add ? mac.add + unit * mac.add_ustride + (int64_t)limb * n : nullptr;
+        const int64_t *a1 = a0 ? a0 + per : nullptr;
+        const int64_t *l0 = mac.add0 ? mac.add0 + unit * mac.add0_ustride + (int64_t)limb * n : nullptr;
+        for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+            // positions 2i, 2i+1 were accumulated by other threads of this CTA: the barrier after the last digit orders them
+            const uint2 u = ACC_SMEM ? acc[2 * i] : __ldcg(acc + 2 * i), v = ACC_SMEM ? acc[2 * i + 1] : __ldcg(acc + 2 * i + 1);
+            uint32_t r00 = u.x, r01 = v.x, r10 = u.y, r11 = v.y;      // r[c][column]
+            if (a0) {
+                const int4 x0 = __ldcs(reinterpret_cast<const int4 *>(a0) + i), x1 = __ldcs(reinterpret_cast<const int4 *>(a1) + i);
+                r00 = ab_addmod(r00, (uint32_t)x0.x, q); r01 = ab_addmod(r01, (uint32_t)x0.z, q);
+                r10 = ab_addmod(r10, (uint32_t)x1.x, q); r11 = ab_addmod(r11, (uint32_t)x1.z, q);
+            }
+            if (l0) {
+                const int4 x0 = __ldcs(reinterpret_cast<const int4 *>(l0) + i);
+                r00 = ab_addmod(r00, (uint32_t)x0.x, q); r01 = ab_addmod(r01, (uint32_t)x0.z, q);
+            }
+            __stcs(reinterpret_cast<int4 *>(o0) + i, make_int4((int)r00, 0, (int)r01, 0));
+            __stcs(reinterpret_cast<int4 *>(o1) + i, make_int4((int)r10, 0, (int)r11, 0));
+        }
+    }
+}
+
+#if AB_MX_MAC_SMEM
+void ab_mx_launch_mac_smem(dim3 grid, int T, size_t smem, cudaStream_t st, const MxArgs &args, const AbMxMac &mac) {
+#else
+void ab_mx_launch_mac_glob(dim3 grid, int T, size_t smem, cudaStream_t st, const MxArgs &args, const AbMxMac &mac) {
+#endif
+    static thread_local bool ready = false;
+    if (!ready) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_mixed_mac<256, AB_MX_MINB, AB_MX_MAC_SMEM != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ready = true;
+    }
+    k_crt_mixed_mac<256, AB_MX_MINB, AB_MX_MAC_SMEM != 0><<<grid, T, smem, st>>>(args, mac);
+}
