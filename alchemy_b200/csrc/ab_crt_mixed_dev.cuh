@@ -333,12 +333,10 @@ __device__ __forceinline__ void mx_load_digit(const AbMxFused &fx, int d, int64_
 
 // Two-phase digit load for the fused inner product with a BaseBGad gadget, where the nd digits of one source limb
 // all come from the same centred coefficients: phase A gathers them ONCE per (k, source limb) -- the only place
-// with dependent loads (index table, then coefficient), issued four at a time -- and parks t = centred + H as
-// int64 in a scratch slice owned by this CTA; phase B cuts digit d out of t with shifts (power-of-two base) or
+// with dependent loads (index table, then coefficient), issued four at a time -- and parks the gathered residues as
+// uint32 in a scratch slice owned by this CTA (half the L2 footprint of an int64 t); phase B forms t = centred + H and cuts digit d out of it with shifts (power-of-two base) or
 // divisions and reduces it into this CTA's modulus.  Thread t touches the same positions in both phases.
-__device__ __forceinline__ void mx_gather_centered(const AbMxFused &fx, int d0, int64_t su, int krow, int n, int64_t *__restrict__ tbuf) {
-    const uint32_t qs = fx.dig[d0].q_src;
-    const int64_t H = fx.dig[d0].H;
+__device__ __forceinline__ void mx_gather_centered(const AbMxFused &fx, int d0, int64_t su, int krow, int n, uint32_t *__restrict__ tbuf) {
     const int32_t *__restrict__ gt = fx.gather ? fx.gather + (int64_t)krow * n : nullptr;
     const int64_t *__restrict__ src = fx.src + su * fx.src_ustride + (int64_t)fx.dig[d0].limb * fx.n_src;
     const int T = blockDim.x;
@@ -355,11 +353,13 @@ __device__ __forceinline__ void mx_gather_centered(const AbMxFused &fx, int d0, 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u * T;
-            if (j < n) __stcg(tbuf + j, (int64_t)ab_center(v[u], qs) + H);
+            if (j < n) __stcg(tbuf + j, v[u]);
         }
     }
 }
-__device__ __forceinline__ void mx_digit_from_t(const AbMxFused &fx, int d, int n, uint32_t q, const int64_t *__restrict__ tbuf, uint32_t *sm) {
+__device__ __forceinline__ void mx_digit_from_t(const AbMxFused &fx, int d, int n, uint32_t q, const uint32_t *__restrict__ tbuf, uint32_t *sm) {
+    const uint32_t qs = fx.dig[d].q_src;
+    const int64_t H = fx.dig[d].H;
     const int lastd = fx.dig[d].last, gb = fx.gbase, hb = fx.gbase / 2;
     const uint32_t pw = fx.dig[d].pw;
     const int pw_shift = (gb > 0 && (gb & (gb - 1)) == 0) ? 31 - __clz((int)pw) : -1;
@@ -368,25 +368,27 @@ __device__ __forceinline__ void mx_digit_from_t(const AbMxFused &fx, int d, int 
         // power-of-two base, inner digit: the wanted bits of floor(t / 2^s) sit in the low word of t (two's complement),
         // and |digit| <= b/2 < q needs no reduction
         const uint32_t mask = (uint32_t)gb - 1u;
-        auto dig = [&](int lo) {
-            const int32_t c = (int32_t)(((uint32_t)lo >> pw_shift) & mask) - hb;
+        const uint32_t Hlo = (uint32_t)H;
+        auto dig = [&](uint32_t v) {
+            const uint32_t lo = (uint32_t)ab_center(v, qs) + Hlo;           // low word of t = centred + H
+            const int32_t c = (int32_t)((lo >> pw_shift) & mask) - hb;
             return c < 0 ? q + (uint32_t)c : (uint32_t)c;
         };
-        // four consecutive positions per thread: two 16-byte loads of t, one 16-byte shared store
+        // four consecutive positions per thread: one 16-byte load of the gathered residues, one 16-byte shared store
         const int n4 = n >> 2;
-        const int4 *t4 = reinterpret_cast<const int4 *>(tbuf);
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(tbuf);
         uint4 *s4 = reinterpret_cast<uint4 *>(sm);
         for (int g = threadIdx.x; g < n4; g += T) {
-            const int4 a = __ldcg(t4 + 2 * g), b = __ldcg(t4 + 2 * g + 1);
-            s4[g] = make_uint4(dig(a.x), dig(a.z), dig(b.x), dig(b.z));
+            const uint4 a = __ldcg(t4 + g);
+            s4[g] = make_uint4(dig(a.x), dig(a.y), dig(a.z), dig(a.w));
         }
-        for (int j = 4 * n4 + threadIdx.x; j < n; j += T) sm[j] = dig((int)__ldcg(tbuf + j));
+        for (int j = 4 * n4 + threadIdx.x; j < n; j += T) sm[j] = dig(__ldcg(tbuf + j));
         return;
     }
     for (int j0 = threadIdx.x; j0 < n; j0 += 4 * T) {
         int64_t t[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) t[u] = (j0 + u * T < n) ? __ldcg(tbuf + j0 + u * T) : 0;
+        for (int u = 0; u < 4; ++u) t[u] = (j0 + u * T < n) ? (int64_t)ab_center(__ldcg(tbuf + j0 + u * T), qs) + H : 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u * T;

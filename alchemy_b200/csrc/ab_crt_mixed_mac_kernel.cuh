@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
         for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    int64_t *tbuf = (mac.tbuf && fx.gbase != 0) ? mac.tbuf + (slice * args.nlimbs + limb) * (int64_t)n : nullptr;
+    uint32_t *tbuf = (mac.tbuf && fx.gbase != 0) ? reinterpret_cast<uint32_t *>(mac.tbuf) + (slice * args.nlimbs + limb) * (int64_t)nb : nullptr;
     const uint2 *hm = reinterpret_cast<const uint2 *>(mac.hm) + (int64_t)limb * n;
     const int64_t hstride = (int64_t)args.nlimbs * n;
     bool first = true;

@@ -206,7 +206,7 @@ struct AbMxMac {
     const int64_t *add0;         // optional [unit][L][n] added to component 0 (tunnel: the evalLin part)
     int64_t add0_ustride;
     void *acc;                   // scratch of ab_mixed_mac_scratch_words() int64 words (may be null when that is 0)
-    int64_t *tbuf;               // optional scratch [unit][L][n] int64: centred source + H, gathered once per (k, source limb)
+    int64_t *tbuf;               // optional scratch of [unit][parts][L][n] int64 words (used as uint32: the source residues gathered once per (k, source limb))
     int64_t *out;                // [unit][2][L][n]
     int64_t out_ustride;
 };
