@@ -172,7 +172,7 @@ def mul_keyswitch_leg(ab, torch, iters=5):
     from alchemy_b200 import she
     out = []
     for name, m, moduli, lin, lh, lout, B in (
-            ("HomomRLWR level 1", 20475, [1543651201, 689270401, 718099201, 720720001, 1556755201, 1567238401], 4, 5, 3, 256),
+            ("HomomRLWR level 1", 20475, [1543651201, 689270401, 718099201, 720720001, 1556755201, 1567238401], 4, 5, 3, 1024),
             ("Arithmetic", 512, [268440577, 8392193, 1073750017], 2, 2, 1, 16384)):
         plan = ab.Plan(m, moduli)
         n = plan.n

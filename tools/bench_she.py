@@ -43,8 +43,8 @@ def timeit(fn, iters):
 def mul_cases(iters):
     out = []
     for name, m, moduli, lin, lh, lout, B in (
-            ("HomomRLWR mul level 1", 20475, RLWR_Q, 4, 5, 3, 512), ("HomomRLWR mul level 2", 20475, RLWR_Q, 3, 4, 2, 512),
-            ("HomomRLWR mul level 3", 20475, RLWR_Q, 2, 3, 1, 1024), ("HomomRLWR mul level 4", 20475, RLWR_Q, 1, 2, 1, 1024),
+            ("HomomRLWR mul level 1", 20475, RLWR_Q, 4, 5, 3, 2048), ("HomomRLWR mul level 2", 20475, RLWR_Q, 3, 4, 2, 2048),
+            ("HomomRLWR mul level 3", 20475, RLWR_Q, 2, 3, 1, 2048), ("HomomRLWR mul level 4", 20475, RLWR_Q, 1, 2, 1, 2048),
             ("Arithmetic mul", 512, ARITH_Q, 2, 2, 1, 32768)):
         plan = ab.Plan(m, moduli)
         n = plan.n
