@@ -252,3 +252,43 @@ def _digits(q, base):
         v *= base
         k += 1
     return k
+
+
+def tunnelHint(tn, ext_er, moduli, s_in_crt, s_out_crt, flin, mask, noise_dec, base=0):
+    """Lol `tunnelHint` (KeysHints.hs:113): hint[k, d] = (b, a) with b + a s_out = gamma_d * f(relpow_k * s_in) + e_{k,d}.
+    tn: she.Tunnel for (r', e', s'); ext_er: Ext(e', r') over the same moduli; s_in_crt [L, n_r], s_out_crt [L, n_s] (CRT);
+    flin [K, L, n_s]; mask [K, D, L, n_s] uniform; noise_dec [K, D, n_s] small integers (decoding basis of O_s').
+    f(relpow_k * s_in) is obtained from the tunnel kernel itself: tunnelling the degree-0 ciphertext (x, 0) yields (f(x), 0)."""
+    pr, ps = tn.r, tn.s
+    K, D, L, ns = mask.shape
+    nr = pr.n
+    dev = mask.device
+    # relpow_k = uncoeffs of the k-th unit vector over O_e' (powerful basis), times s_in, as degree-0 ciphertexts
+    onehot = torch.zeros((K, K, L, ext_er.lo.n), dtype=torch.int64, device=dev)
+    for k in range(K):
+        onehot[k, k, :, 0] = 1
+    rel = GT.uncoeffs(ext_er, onehot, nlimbs=L)                       # [K, L, n_r]
+    GT.crt(pr, rel, nlimbs=L)
+    GT.mul(pr, rel, s_in_crt[:L].unsqueeze(0).contiguous(), nlimbs=L)
+    c = torch.zeros((K, 2, L, nr), dtype=torch.int64, device=dev)
+    c[:, 0] = rel
+    zero_hint = torch.zeros((K, D, 2, L, ns), dtype=torch.int64, device=dev)
+    target = tn(c, flin, zero_hint, base)[:, 0].contiguous()           # [K, L, n_s] = f(relpow_k s_in), CRT basis of O_s'
+    # b = e - a s_out (+ gamma_d * target in the limb the gadget element lives in)
+    e = torch.empty((K * D, L, ns), dtype=torch.int64, device=dev)
+    check(lib().ab_lift_plain_dev(ps.h, _ptr(e), _ptr(noise_dec.reshape(K * D, ns).contiguous()), K * D, L, LIFT_ALL, _stream()))
+    GT.crt(ps, GT.l(ps, e, nlimbs=L), nlimbs=L)
+    t = mask.reshape(K * D, L, ns).clone()
+    GT.mul(ps, t, s_out_crt[:L].unsqueeze(0).contiguous(), nlimbs=L)
+    GT.sub(ps, e, t, nlimbs=L)
+    b = e.reshape(K, D, L, ns)
+    d = 0
+    for l, q in enumerate(moduli[:L]):
+        for i in range(_digits(q, base)):
+            g = target[:, l:l + 1].clone()                             # [K, 1, n_s]
+            GT.scalarMul(ps, g, [1 if base == 0 else pow(base, i, q)], limb0=l, nlimbs=1)
+            row = b[:, d, l].contiguous().view(K, 1, ns)
+            GT.add(ps, row, g, limb0=l, nlimbs=1)
+            b[:, d, l] = row[:, 0]
+            d += 1
+    return torch.stack([b, mask], dim=2).contiguous()

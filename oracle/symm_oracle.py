@@ -280,3 +280,40 @@ def mat_inv_mod(G, mod):
                 a[r] = [(x - f * y) % mod for x, y in zip(a[r], a[col])]
                 inv[r] = [(x - f * y) % mod for x, y in zip(inv[r], inv[col])]
     return np.array(inv, dtype=object)
+
+
+# ---- tunnel hint (KeysHints.hs:113 `getTunnelHint`; Lol `tunnelHint` [RECALL]) --------------------------------------------
+def eval_lin(r, e, s_idx, moduli, x_pow, flin):
+    """the E-linear map fixed by flin[k] = f(relative decoding basis element k), applied to x (powerful basis of O_r,
+    [..., L, n_r]) -> CRT basis of O_s: sum_k embed(coeffsDec(x)_k) * flin_k"""
+    qv = _mods(moduli)
+    tab = O.coeff_indices(e, r)
+    dec = S.per_limb(O.l_inv, r, moduli, x_pow)
+    acc = 0
+    for k in range(tab.shape[0]):
+        part = S.per_limb(O.l, e, moduli, dec[..., tab[k]])
+        acc = (acc + S.crt(s_idx, moduli, S.embed_pow(e, s_idx, part)) * flin[k] % qv) % qv
+    return acc
+
+
+def tunnel_hint(r, e, s_idx, moduli, s_in_crt, s_out_crt, flin, mask, noise_dec, base):
+    """hint[k, d] = (b, a) with b + a s_out = gamma_d * f(relpow_k * s_in) + e_{k,d}: key-switches the K = [O_r : O_e]
+    E-coefficients of c1 s_in into O_s.  s_in_crt [L, n_r], s_out_crt [L, n_s] (CRT bases), mask [K, D, L, n_s] uniform,
+    noise_dec [K, D, n_s] small integers in the decoding basis of O_s -> [K, D, 2, L, n_s]"""
+    L = len(moduli)
+    qv = _mods(moduli)
+    tab = O.coeff_indices(e, r)
+    K, nr, ns = tab.shape[0], s_in_crt.shape[-1], s_out_crt.shape[-1]
+    gad = S.gadget_vector(moduli, base)
+    hint = np.zeros((K, len(gad), 2, L, ns), dtype=np.int64)
+    for k in range(K):
+        relpow = np.zeros((L, nr), dtype=np.int64)
+        relpow[:, tab[k][0]] = 1
+        prod_pow = S.crt_inv(r, moduli, S.crt(r, moduli, relpow) * s_in_crt % qv)
+        target = eval_lin(r, e, s_idx, moduli, prod_pow, flin)
+        for d, (l, v) in enumerate(gad):
+            err = S.crt(s_idx, moduli, S.per_limb(O.l, s_idx, moduli, lift_plain(noise_dec[k, d], moduli, 1 << 40)))
+            b = (err - mask[k, d] * s_out_crt % qv) % qv
+            b[l] = (b[l] + target[l] * v) % moduli[l]
+            hint[k, d, 0], hint[k, d, 1] = b, mask[k, d]
+    return hint

@@ -151,3 +151,45 @@ def test_device_randomness_matches_the_cpu_restatement_and_drives_the_circuit():
     want = np.stack([plain_mul(m, p, ((a + b) % p)[None], b[None])[0] for a, b in zip(x, y)])
     assert same(gpu.decrypt(sk, ct), want)
     assert (gpu.errorRate(sk, ct).cpu().numpy() < 0.25).all()
+
+
+@pytest.mark.parametrize("r,e,s_idx,moduli,L,base", [(12, 4, 20, primes_1_mod(60, 1 << 24, 2), 2, 4), (9, 3, 21, primes_1_mod(63, 1 << 24, 2), 2, 0),
+                                                     (11648, 5824, 29120, [537264001, 539884801], 1, 2)])      # Tunnel.hs hop 1, BaseBGad 2
+def test_tunnel_hint_generated_on_the_device(r, e, s_idx, moduli, L, base):
+    """Lol tunnelHint (KeysHints.hs:113) from device kernels: bit-identical to the CPU restatement, and tunnelling with it
+    maps the phase c0 + c1 s_in through the E-linear function up to bounded noise"""
+    from math import prod
+
+    import alchemy_b200 as ab
+    from alchemy_b200 import she, symm
+    from oracle import oracle as O
+    q = moduli[:L]
+    rng = np.random.default_rng(r + s_idx + base)
+    nr, ne, ns = (O.totient(O.factor(x)) for x in (r, e, s_idx))
+    K, D = nr // ne, S.gadget_len(q, base)
+    qv = np.array(q, dtype=np.int64)[:, None]
+    rnd = lambda lead, n: np.stack([rng.integers(0, ql, size=tuple(lead) + (n,)) for ql in q], axis=-2)
+    flin, mask, noise = rnd((K,), ns), rnd((K, D), ns), rng.integers(-2, 3, size=(K, D, ns))
+    s_in = S.crt(r, q, Y.lift_plain(rng.integers(-1, 2, size=nr), q, 1 << 40))
+    s_out = S.crt(s_idx, q, Y.lift_plain(rng.integers(-1, 2, size=ns), q, 1 << 40))
+    want_hint = Y.tunnel_hint(r, e, s_idx, q, s_in, s_out, flin, mask, noise, base)
+    pr, ps, pe = ab.Plan(r, q), ab.Plan(s_idx, q), ab.Plan(e, q, crt=False)
+    tn = she.Tunnel(pr, pe, ps)
+    hint = symm.tunnelHint(tn, ab.Ext(pe, pr), q, dev(s_in), dev(s_out), dev(flin), dev(mask), dev(noise), base)
+    assert same(hint, want_hint)
+    c = rnd((2, 2), nr)
+    out = tn(dev(c), dev(flin), hint, base).cpu().numpy()
+    assert (out == S.tunnel(r, e, s_idx, q, c, flin, want_hint, base)).all()
+    phase_in = S.crt_inv(r, q, (c[:, 0] + c[:, 1] * s_in % qv) % qv)
+    want = Y.eval_lin(r, e, s_idx, q, phase_in, flin)
+    got = (out[:, 0] + out[:, 1] * s_out % qv) % qv
+    diff = S.crt_inv(s_idx, q, (got - want) % qv)
+    Q = prod(q)
+    acc = np.zeros((2, ns), dtype=object)
+    for l, ql in enumerate(q):
+        Ql = Q // ql
+        acc = (acc + diff[:, l].astype(object) * (Ql * pow(Ql, -1, ql))) % Q
+    err = np.where(acc * 2 > Q, acc - Q, acc)
+    digit = max(q) // 2 + 1 if base == 0 else base
+    bound = K * D * ns * 8 * digit * 2 * 13
+    assert (abs(err) <= bound).all()

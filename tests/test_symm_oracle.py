@@ -92,3 +92,34 @@ def test_mod_switch_pt_divides_the_plaintext():
     ct = sch.mod_switch_pt(sch.encrypt(sk, x["mu"], x["noise"], x["c1"]), p2)
     got = Y.SymmSHE(m, mp, moduli, p2).decrypt(sk, ct)
     assert (got == x["mu"] // 2).all()
+
+
+def test_tunnel_with_generated_hint_maps_the_phase():
+    """tunnel_hint + S.tunnel: the phase of the output is f(phase of the input) up to bounded noise (no GPU)"""
+    from math import lcm, prod
+    r, e, s_idx, base = 12, 4, 20, 4
+    moduli = primes_1_mod(lcm(r, s_idx), 1 << 24, 2)
+    L = len(moduli)
+    nr, ne, ns = (O.totient(O.factor(x)) for x in (r, e, s_idx))
+    K, D = nr // ne, S.gadget_len(moduli, base)
+    rng = np.random.default_rng(77)
+    qv = np.array(moduli, dtype=np.int64)[:, None]
+    rnd = lambda lead, n: np.stack([rng.integers(0, q, size=tuple(lead) + (n,)) for q in moduli], axis=-2)
+    flin = rnd((K,), ns)
+    s_in = S.crt(r, moduli, Y.lift_plain(rng.integers(-1, 2, size=nr), moduli, 1 << 40))
+    s_out = S.crt(s_idx, moduli, Y.lift_plain(rng.integers(-1, 2, size=ns), moduli, 1 << 40))
+    hint = Y.tunnel_hint(r, e, s_idx, moduli, s_in, s_out, flin, rnd((K, D), ns), rng.integers(-2, 3, size=(K, D, ns)), base)
+    c = rnd((2, 2), nr)
+    out = S.tunnel(r, e, s_idx, moduli, c, flin, hint, base)
+    phase_in = S.crt_inv(r, moduli, (c[:, 0] + c[:, 1] * s_in % qv) % qv)
+    want = Y.eval_lin(r, e, s_idx, moduli, phase_in, flin)
+    got = (out[:, 0] + out[:, 1] * s_out % qv) % qv
+    diff = S.crt_inv(s_idx, moduli, (got - want) % qv)
+    Q = prod(moduli)
+    acc = np.zeros((2, ns), dtype=object)
+    for l, q in enumerate(moduli):
+        Ql = Q // q
+        acc = (acc + diff[:, l].astype(object) * (Ql * pow(Ql, -1, q))) % Q
+    err = np.where(acc * 2 > Q, acc - Q, acc)
+    bound = K * D * ns * 8 * base * 2 * ns
+    assert (abs(err) <= bound).all() and Q > 1000 * bound
