@@ -3,9 +3,9 @@
 // The reference reaches them at Crypto/Alchemy/Interpreter/Eval.hs:65-67 ((*) on CT), :130
 // (modSwitch), :133 (keySwitchQuadCirc), :134 (tunnel); PT2CT.hs:172-177 and :224-229 fix the order
 // in which they are chained.  Upstream performs them in Haskell on top of one-element Tensor calls
-// [RECALL]; here each is a handful of launches over the whole batch, with every intermediate in a
-// caller-supplied scratch buffer that is sized to stay L2-resident (the batch is processed in
-// chunks).  All polynomials are in the CRT basis, PLANAR layout: c[b][i][l][j].
+// [RECALL]; here each is a handful of launches over the whole batch, with the few intermediates that
+// leave the SMs in a caller-supplied scratch buffer (`*_work_bytes`; very large batches are processed in
+// chunks of that size).  All polynomials are in the CRT basis, PLANAR layout: c[b][i][l][j].
 #include <algorithm>
 #include <cstdlib>
 
