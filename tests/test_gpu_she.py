@@ -67,6 +67,7 @@ MULS = [  # (m, moduli, L_in, L_hint, L_out, base): the limb schedule of SURVEY.
     (1024, [1073479681, 1052835841, 1032192001], 2, 3, 1, 0),
     (2048, [1073479681, 1052835841, 1032192001], 2, 3, 2, 0),
     (8192, [1073479681, 1052835841, 1032192001], 2, 3, 1, 0),   # too large for shared memory: the launch sequence behind the same entry
+    (45, [181, 541, 631], 3, 2, 1, 0), (64, [193, 257, 449], 3, 2, 1, 0),   # hint modulus SMALLER than the input's: rescale down before the key switch
 ]
 
 
@@ -171,3 +172,36 @@ def test_full_size_roundtrip_properties():
     c3b[:, 0] = (c3b[:, 0] + d0) % qv
     o2 = she.keySwitchQuadCirc(plan, c3b, hint)
     assert torch.equal((o2[:, 0] - o1[:, 0]) % qv, d0) and torch.equal(o2[:, 1], o1[:, 1])
+
+
+def test_empty_batches_and_bad_arguments_of_the_fused_entries():
+    """batch = 0 is a no-op with status 0; null pointers / limb counts outside the plan are AB_ERR_ARG, never a crash"""
+    import ctypes as C
+
+    import torch
+
+    import alchemy_b200 as ab
+    lib = ab.lib()
+    plan = ab.Plan(45, [181, 541, 631])
+    z = torch.zeros(8, dtype=torch.int64, device="cuda")
+    p = C.c_void_p(z.data_ptr())
+    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 0, 2, 3, 1, 0, None, None) == 0
+    assert lib.ab_ct_phase_dev(plan.h, p, p, p, 0, 2, 2, None) == 0
+    assert lib.ab_rns_lift_reduce_dev(plan.h, p, None, p, 0, 2, 7, None) == 0
+    assert lib.ab_lift_plain_dev(plan.h, p, p, 0, 2, 7, None) == 0
+    assert lib.ab_ct_add_public_dev(plan.h, p, p, 0, 2, 2, None) == 0 and lib.ab_ct_mul_public_dev(plan.h, p, p, 0, 2, 2, None) == 0
+    assert lib.ab_uniform_dev(plan.h, p, 0, 2, 1, 0, None) == 0
+    assert lib.ab_mul_key_switch_dev(plan.h, None, p, p, p, 1, 2, 3, 1, 0, p, None) == ab._lib.AB_ERR_ARG
+    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 1, 2, 4, 1, 0, p, None) == ab._lib.AB_ERR_ARG          # 4 limbs > plan
+    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 1, 2, 3, 1, 0, None, None) == ab._lib.AB_ERR_ARG       # scratch missing
+    assert lib.ab_rns_lift_reduce_dev(plan.h, p, None, p, 1, 2, 1, None) == ab._lib.AB_ERR_ARG                  # modulus 1
+    assert lib.ab_gaussian_dev(plan.h, p, 1, None, 4, 1, 0, None) == ab._lib.AB_ERR_ARG
+    assert lib.ab_mul_key_switch_work_bytes(plan.h, 4, 2, 3, 1, 0) > 0 and lib.ab_mul_key_switch_work_bytes(plan.h, 4, 2, 9, 1, 0) == -1
+    # composite plaintext moduli: L / mulG work, divG refuses when an odd prime of m is not invertible
+    p9 = ab.Plan(45, [9], crt=False)
+    y = torch.arange(p9.n, dtype=torch.int64, device="cuda").reshape(1, 1, -1) % 9
+    keep = y.clone()
+    ab.GT.lInv(p9, ab.GT.l(p9, y))
+    assert torch.equal(y, keep)
+    with pytest.raises(ab.AlchemyError):
+        ab.GT.divGPow(p9, y)
