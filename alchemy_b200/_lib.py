@@ -19,6 +19,12 @@ class PrimeExp(C.Structure):
     _fields_ = [("prime", C.c_int32), ("exponent", C.c_int32)]
 
 
+class WireHeader(C.Structure):
+    _fields_ = [("magic", C.c_uint32), ("version", C.c_uint16), ("kind", C.c_uint16), ("m", C.c_int64), ("n", C.c_int64), ("batch", C.c_int64),
+                ("npoly", C.c_int32), ("nlimbs", C.c_int32), ("enc", C.c_int32), ("k", C.c_int32), ("l", C.c_int64), ("pmod", C.c_int64),
+                ("moduli", C.c_int64 * 8), ("checksum", C.c_uint64)]
+
+
 class AlchemyError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"alchemy_b200 error {code}: {msg}")
@@ -88,6 +94,10 @@ SIGNATURES = {
     "ab_lift_plain_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "ab_uniform_dev": (C.c_int, [_vp, _vp, _i64, _i32, C.c_uint64, C.c_uint32, _vp]),
     "ab_gaussian_dev": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_uint64), _i32, C.c_uint64, C.c_uint32, _vp]),
+    "ab_wire_bytes": (_i64, [C.POINTER(WireHeader)]),
+    "ab_wire_pack_dev": (C.c_int, [_vp, C.POINTER(WireHeader), _vp, _vp]),
+    "ab_wire_read_header": (C.c_int, [C.POINTER(WireHeader), _vp, _i64]),
+    "ab_wire_unpack_dev": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ab_tensor_op_host": (C.c_int, [_vp, C.c_int, _vp, _i64, C.c_int]),
     "ab_mul_host": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int]),
     "tensorCRTRq": (C.c_int, [C.c_int16, _vp, _i64, C.POINTER(PrimeExp), C.c_int16, C.POINTER(_vp), C.POINTER(_i64)]),

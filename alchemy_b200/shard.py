@@ -29,9 +29,11 @@ def scatter_units(full, world=None, rank=None):
     return full[lo:hi]
 
 
-def gather_units(local, total, dst=None):
+def gather_units(local, total, dst=None, packed=False):
     """concatenate every rank's result along the batch axis (ragged shards allowed).
-    dst=None: all ranks get the result (all_gather); dst=r: only rank r (others get None)."""
+    dst=None: all ranks get the result (all_gather); dst=r: only rank r (others get None).
+    packed=True (CUDA int64 residues only): every shard travels in the wire format (alchemy_b200/wire.py: one uint32 per
+    residue plus a checksummed header) -- half the NVLink bytes of the int64 tensors; the receiver verifies each shard."""
     world, rank = dist.get_world_size(), dist.get_rank()
     sizes = shard_sizes(total, world)
     assert local.shape[0] == sizes[rank], (local.shape, sizes, rank)
@@ -41,6 +43,22 @@ def gather_units(local, total, dst=None):
         buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         buf[:local.shape[0]] = local
     buf = buf.contiguous()
+    rest = 1
+    for d in local.shape[1:]:
+        rest *= int(d)
+    if packed and local.is_cuda and local.dtype == torch.int64 and 0 < rest < (1 << 24):
+        from . import wire
+        w = wire.pack("elements", 1, buf.reshape(pad, 1, 1, rest), [])
+        if dst is None:
+            got = [torch.empty_like(w) for _ in range(world)]
+            dist.all_gather(got, w)
+        else:
+            got = [torch.empty_like(w) for _ in range(world)] if rank == dst else None
+            dist.gather(w, got, dst=dst)
+            if rank != dst:
+                return None
+        parts = [wire.unpack(g)[1].reshape((pad,) + tuple(local.shape[1:])) for g in got]
+        return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
     if dst is None:
         parts = [torch.empty_like(buf) for _ in range(world)]
         dist.all_gather(parts, buf)

@@ -199,6 +199,27 @@ int ab_lift_plain_dev(const ab_plan *p, int64_t *out, const int64_t *in, int64_t
 int ab_uniform_dev(const ab_plan *p, int64_t *out, int64_t batch, int32_t nlimbs, uint64_t seed, uint32_t stream_id, void *stream);
 int ab_gaussian_dev(const ab_plan *p, int64_t *out, int64_t batch, const uint64_t *cdt, int32_t cdt_len, uint64_t seed, uint32_t stream_id, void *stream);
 
+/* ---- wire / on-disk format (upstream: none -- keys and hints are in-memory Dynamics, KeysHints.hs:36-39) -------------
+ * 136-byte little-endian header, then one uint32 per residue in the device layout [batch][npoly][nlimbs][n]
+ * (residues are below 2^31: half the bytes of the int64 tensors on NVLink / PCIe / disk). */
+typedef struct {
+    uint32_t magic;            /* "AB2W"; filled in by ab_wire_pack_dev */
+    uint16_t version, kind;    /* kind: 1 ring elements, 2 ciphertexts, 3 key-switch hint, 4 tunnel hint */
+    int64_t m, n, batch;       /* cyclotomic index of the polynomials, phi(m), leading dimension */
+    int32_t npoly, nlimbs;     /* polynomials per unit (ciphertext: degree + 1; hint row: 2), RNS limbs */
+    int32_t enc, k;            /* SymmSHE bookkeeping of ciphertexts: 0 LSD / 1 MSD, power of g */
+    int64_t l, pmod;           /* scalar l, plaintext modulus */
+    int64_t moduli[8];
+    uint64_t checksum;         /* sum of all residues mod 2^64; filled in by ab_wire_pack_dev, verified by ab_wire_unpack_dev */
+} ab_wire_header;
+int64_t ab_wire_bytes(const ab_wire_header *h);                    /* header + payload */
+/* wire_dev: DEVICE buffer of ab_wire_bytes(h) bytes, 8-byte aligned; h: HOST header (magic/version/checksum are overwritten) */
+int ab_wire_pack_dev(void *wire_dev, const ab_wire_header *h, const int64_t *data_dev, void *stream);
+/* validates magic, version and that wire_bytes matches the header; synchronous */
+int ab_wire_read_header(ab_wire_header *h_out, const void *wire_dev, int64_t wire_bytes);
+/* unpacks into data_dev ([batch][npoly][nlimbs][n] int64) and verifies the checksum; returns after the check */
+int ab_wire_unpack_dev(int64_t *data_dev, const void *wire_dev, int64_t wire_bytes, void *stream);
+
 /* ---- host-buffer entries: what a `foreign import ccall` from Lol's CPP.hs would bind ------------
  * lol-cpp shape [RECALL]: void tensorCRTRq(hShort_t tupSize, Zq* y, hDim_t totm, PrimeExponent* pe,
  *                                         hShort_t sizeOfPE, Zq** ru, hInt_t* qs)

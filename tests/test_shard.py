@@ -52,3 +52,39 @@ def test_world_size_2_gloo_scatter_compute_gather(total):
     for p in procs:
         p.join(timeout=60)
     assert results == [(0, True), (1, True)]
+
+
+def _nccl_worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g = torch.Generator().manual_seed(3)
+        full = torch.randint(0, 1 << 31, (total, 2, 3, 64), dtype=torch.int64, generator=g).cuda()
+        mine = shard.scatter_units(full).clone()
+        ok = torch.equal(shard.gather_units(mine, total, packed=True), full)
+        at0 = shard.gather_units(mine, total, dst=0, packed=True)
+        ok = ok and ((at0 is None) if rank else torch.equal(at0, full))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("total", [9, 2])
+def test_packed_gather_over_nccl(total):
+    """results gathered in the wire format (uint32 payload, checksummed): as many ranks as there are GPUs, at most two"""
+    world = min(2, torch.cuda.device_count())
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert results == [(r, True) for r in range(world)]
