@@ -99,11 +99,64 @@ def tunnel_chain(total, iters, rank, world):
             "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / PEAK, "launches_per_call": int((ab.lib().ab_kernel_launches() - l0) // (iters + 2))}
 
 
+def rlwr_chain(B, iters):
+    """examples/HomomRLWR.hs as a chain of device calls on synthetic ciphertexts and hints: mulPublic,
+    five ring-tunnelling hops H0' -> ... -> H5' (TrivGad; modSwitch to the hint modulus, tunnel, modSwitch back: 5 -> 6 -> 5 limbs,
+    last hop 5 -> 5 -> 4), then the rescaling tree at H5': 8 `mul_` pipelines (1 + 4 + 2 + 1 over the four levels), 15 div2
+    (bookkeeping only in MSD form) and 9 addPublic.  One unit = one evaluation of the whole circuit on one ciphertext."""
+    import ctypes as C
+    Q = RLWR_Q
+    idx = [11648, 29120, 43680, 54600, 27300, 20475]
+    es = [5824, 14560, 10920, 27300, 6825]
+    plans = {m: ab.Plan(m, Q) for m in idx}
+    hops = []
+    for i in range(5):
+        r, s, e = idx[i], idx[i + 1], es[i]
+        lh, lout = (6, 5) if i < 4 else (5, 4)
+        t = she.Tunnel(plans[r], ab.Plan(e, Q, crt=False), plans[s])
+        D = ab.GT.gadgetLen(plans[s], lh, 0)
+        hops.append((t, s, lh, lout, rnd(Q[:lh], (t.K,), plans[s].n), rnd(Q[:lh], (t.K, D, 2), plans[s].n)))
+    p5 = plans[20475]
+    n5 = p5.n
+    levels = [(4, 5, 3, 1), (3, 4, 2, 4), (2, 3, 1, 2), (1, 2, 1, 1)]          # (L_in, L_hint, L_out, how many)
+    hints = [rnd(Q[:lh], (lh, 2), n5) for _, lh, _, _ in levels]
+    x0 = rnd(Q[:5], (B, 2), plans[11648].n)
+    pub = rnd(Q[:5], (1,), plans[11648].n)[0].contiguous()
+    pub5 = [rnd(Q[:lin], (1,), n5)[0].contiguous() for lin, _, _, _ in levels]
+    lib = ab.lib()
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+
+    def run():
+        c = x0.clone()
+        ab.check(lib.ab_ct_mul_public_dev(plans[11648].h, ptr(c), ptr(pub), B, 2, 5, st()))
+        for t, s, lh, lout, flin, hint in hops:
+            c = she.modSwitch(t.r, c, lh)
+            c = t(c, flin, hint, base=0)
+            c = she.modSwitch(plans[s], c, lout)
+        # rescaling tree: level k consumes pairs of level k-1 results; synthetic operands of the right shape per level
+        cur = c                                                      # [B, 2, 4, n5]
+        for (lin, lh, lout, count), hint, pb in zip(levels, hints, pub5):
+            a = cur[:, :, :lin].contiguous()
+            outs = []
+            for _ in range(count):
+                b = a.clone()
+                ab.check(lib.ab_ct_add_public_dev(p5.h, ptr(b), ptr(pb), B, 2, lin, st()))      # the (z_i + y) leaves / node operands
+                outs.append(she.mulKeySwitch(p5, a, b, hint, lh, lout))
+            cur = outs[0]
+        return cur
+    l0 = lib.ab_kernel_launches()
+    ms = timeit(run, iters)
+    return {"case": "HomomRLWR.hs evaluation chain (mulPublic, 5 tunnel hops, 8 mul_ pipelines, TrivGad)", "B": B, "ms": ms,
+            "evaluations_per_s": B / (ms * 1e-3), "launches_per_call": int((lib.ab_kernel_launches() - l0) // (iters + 2))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--ciphertexts", type=int, default=4096)
-    ap.add_argument("--cases", default="mul,tunnel")
+    ap.add_argument("--cases", default="mul,rlwr,tunnel")
+    ap.add_argument("--rlwr-batch", type=int, default=1024)
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -112,6 +165,8 @@ def main():
     if "mul" in args.cases and rank == 0:
         for r in mul_cases(args.iters):
             print(json.dumps(r), flush=True)
+    if "rlwr" in args.cases and rank == 0:
+        print(json.dumps(rlwr_chain(args.rlwr_batch, args.iters)), flush=True)
     if "tunnel" in args.cases:
         r = tunnel_chain(args.ciphertexts, args.iters, rank, world)
         if rank == 0:
