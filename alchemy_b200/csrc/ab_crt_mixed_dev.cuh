@@ -245,9 +245,9 @@ __device__ __forceinline__ void radix2_item(uint32_t *sm, const uint32_t *__rest
 __host__ __device__ constexpr bool mx_contig_span(int P, bool wide) { return (P == 4 || P == 6) || (!wide && (P == 10 || P == 12)); }
 
 template <bool INV, bool WIDE>
-__device__ __forceinline__ void run_program(const MxArgs &args, uint32_t *sm, const uint32_t *tab, uint32_t q, uint32_t qinv_neg) {
+__device__ __forceinline__ void run_program(const MxArgs &args, uint32_t *sm, const uint32_t *tab, uint32_t q, uint32_t qinv_neg, int first_step = 0) {
     const bool contig_ok = ((uintptr_t)sm & 15) == 0;     // vector accesses need the residue buffer 16-byte aligned
-    for (int si = 0; si < args.nsteps; ++si) {
+    for (int si = first_step; si < args.nsteps; ++si) {
         const AbMxStep &s = args.steps[si];
         const int nw = s.nwork / s.vec;
         if (s.kind == 0) {
@@ -404,6 +404,71 @@ __device__ __forceinline__ void mx_digit_from_t(const AbMxFused &fx, int d, int 
                 sm[j] = mx_reduce_signed(c, q);
             }
         }
+    }
+}
+
+// Binary gadget digit d (base 2, not the last digit) of the gathered residues, and the FIRST forward step on it, in one pass:
+// the digit of position j is bit d of t = centred(v_j) + H minus one, i.e. -1 or 0, so the P-point step of an item is minus the
+// sum of the matrix columns whose digit is -1 -- two table lookups per output (ab_internal.h mx_bits_lut) instead of P
+// multiply-adds and a reduction, and the digit never goes through shared memory.  Items are P consecutive positions.
+template <int P>
+__device__ __forceinline__ void mx_bits_first_step(const AbMxFused &fx, int d, int n, uint32_t q, const uint32_t *__restrict__ tbuf,
+                                                   const uint32_t *__restrict__ lut, uint32_t *sm) {
+    constexpr int H2 = (P + 1) / 2, SUB = 1 << H2;
+    const uint32_t qs = fx.dig[d].q_src, Hlo = (uint32_t)fx.dig[d].H;
+    const int sh = 31 - __clz((int)fx.dig[d].pw);
+    const int items = n / P;
+    for (int v = threadIdx.x; v < items; v += blockDim.x) {
+        const uint32_t *src = tbuf + v * P;
+        uint32_t w[P];
+        if (P % 4 == 0) {
+            mx_static_for<(P % 4 == 0 ? P / 4 : 0)>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                const uint4 t = __ldcg(reinterpret_cast<const uint4 *>(src) + k);
+                w[(4 * k) % P] = t.x; w[(4 * k + 1) % P] = t.y; w[(4 * k + 2) % P] = t.z; w[(4 * k + 3) % P] = t.w;
+            });
+        } else {
+            mx_static_for<(P % 2 == 0 ? P / 2 : 0)>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                const uint2 t = __ldcg(reinterpret_cast<const uint2 *>(src) + k);
+                w[(2 * k) % P] = t.x; w[(2 * k + 1) % P] = t.y;
+            });
+        }
+        uint32_t m0 = 0, m1 = 0;       // bit c set <=> digit of column c is -1 <=> bit d of t is clear
+        mx_static_for<P>([&](auto C) {
+            constexpr int c = decltype(C)::value;
+            const uint32_t lo = (uint32_t)ab_center(w[c], qs) + Hlo;
+            const uint32_t neg = ((lo >> sh) & 1u) ^ 1u;
+            if (c < H2) m0 |= neg << (c % H2);
+            else m1 |= neg << ((c - H2) % H2);
+        });
+        uint32_t o[P];
+        mx_static_for<P>([&](auto R) {
+            constexpr int r = decltype(R)::value;
+            o[r] = ab_addmod(__ldg(lut + r * SUB + m0), __ldg(lut + (P + r) * SUB + m1), q);
+        });
+        uint32_t *e = sm + v * P;
+        if (P % 4 == 0) {
+            mx_static_for<(P % 4 == 0 ? P / 4 : 0)>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                reinterpret_cast<uint4 *>(e)[k] = make_uint4(o[(4 * k) % P], o[(4 * k + 1) % P], o[(4 * k + 2) % P], o[(4 * k + 3) % P]);
+            });
+        } else {
+            mx_static_for<(P % 2 == 0 ? P / 2 : 0)>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                reinterpret_cast<uint2 *>(e)[k] = make_uint2(o[(2 * k) % P], o[(2 * k + 1) % P]);
+            });
+        }
+    }
+}
+__device__ __forceinline__ bool mx_bits_dispatch(int P, const AbMxFused &fx, int d, int n, uint32_t q, const uint32_t *tbuf, const uint32_t *lut, uint32_t *sm) {
+    switch (P) {
+        case 2: mx_bits_first_step<2>(fx, d, n, q, tbuf, lut, sm); return true;
+        case 4: mx_bits_first_step<4>(fx, d, n, q, tbuf, lut, sm); return true;
+        case 6: mx_bits_first_step<6>(fx, d, n, q, tbuf, lut, sm); return true;
+        case 10: mx_bits_first_step<10>(fx, d, n, q, tbuf, lut, sm); return true;
+        case 12: mx_bits_first_step<12>(fx, d, n, q, tbuf, lut, sm); return true;
+        default: return false;
     }
 }
 

@@ -65,6 +65,10 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     fill_mx_args(p, args, 0, nlimbs, false, max_words);
     args.batch = units;
     args.estride = 1; args.lstride = p->n; args.bstride = p->n * nlimbs;
+    AbMxMac mac2 = mac;
+    static const bool no_bits = getenv("AB_NO_BITS") && atoi(getenv("AB_NO_BITS")) != 0;      // A/B measurements only
+    mac2.bits_p = no_bits ? 0 : p->mx_bits_p; mac2.bits_h = p->mx_bits_h;
+    for (int l = 0; l < nlimbs; ++l) mac2.bits_lut[l] = (mac2.bits_p && (size_t)l < p->mx_bits_lut.size()) ? p->mx_bits_lut[l] : nullptr;
     const int parts = mac.parts > 1 ? mac.parts : 1;
     const bool acc_smem = parts == 1 && mac_acc_in_smem(p, std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]));
     AB_REQUIRE(acc_smem || mac.acc, AB_ERR_ARG, "fused gadget inner product: scratch missing");
@@ -72,14 +76,14 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     static const int force_t = getenv("AB_MX_MAC_T") ? atoi(getenv("AB_MX_MAC_T")) : 0;      // experiments only
     const int T = force_t ? force_t : pick_threads(p->mx_fwd, (int)p->n, smem);
     const dim3 grid((unsigned)(units * parts), (unsigned)nlimbs);
-    if (acc_smem) ab_mx_launch_mac_smem(grid, T, smem, st, args, mac);
-    else ab_mx_launch_mac_glob(grid, T, smem, st, args, mac);
+    if (acc_smem) ab_mx_launch_mac_smem(grid, T, smem, st, args, mac2);
+    else ab_mx_launch_mac_glob(grid, T, smem, st, args, mac2);
     ab_count_launch();
     ab_check_launch("crt_mixed_mac");
     if (parts > 1) {
         const int64_t work = units * nlimbs * p->n;
         const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)p->sm_count * 16));
-        k_mac_combine<<<g, 256, 0, st>>>(args, mac);
+        k_mac_combine<<<g, 256, 0, st>>>(args, mac2);
         ab_count_launch();
         ab_check_launch("mac_combine");
     }

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
         for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     uint32_t *tbuf = (mac.tbuf && fx.gbase != 0) ? reinterpret_cast<uint32_t *>(mac.tbuf) + (slice * args.nlimbs + limb) * (int64_t)nb : nullptr;
+    // subset-sum tables apply to base 2 with the digits cut from the gathered residues, on a 16-byte aligned residue buffer
+    const uint32_t *bits_lut = (tbuf && fx.gbase == 2 && mac.bits_p > 0 && (n % mac.bits_p) == 0 && ((uintptr_t)sm & 15) == 0) ? mac.bits_lut[limb] : nullptr;
     const uint2 *hm = reinterpret_cast<const uint2 *>(mac.hm) + (int64_t)limb * n;
     const int64_t hstride = (int64_t)args.nlimbs * n;
     bool first = true;
@@ -44,6 +46,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
         for (int kd = kd0; kd < kd1; ++kd) {
             const int k = kd / fx.nd, d = kd - k * fx.nd;
             const bool triv = mx_digit_is_trivial(fx, d, limb);
+            int first_step = 0;
             if (triv) {
                 const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
                 uint2 *dst = reinterpret_cast<uint2 *>(sm);
@@ -56,14 +59,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
                     mx_gather_centered(fx, d, unit, k, n, tbuf);
                     __syncthreads();      // the digit pass reads t with a different thread-to-position map
                 }
-                mx_digit_from_t(fx, d, n, q, tbuf, sm);
+                // binary gadget: digit and first transform step in one pass (subset-sum tables), except for the last digit
+                if (bits_lut && !fx.dig[d].last) first_step = mx_bits_dispatch(mac.bits_p, fx, d, n, q, tbuf, bits_lut, sm) ? 1 : 0;
+                if (!first_step) mx_digit_from_t(fx, d, n, q, tbuf, sm);
             } else {
                 mx_load_digit(fx, d, unit, k, n, q, sm);
             }
             __syncthreads();
             if (!triv) {
-                if (wide) run_program<false, true>(args, sm, tab, q, qinv_neg);
-                else run_program<false, false>(args, sm, tab, q, qinv_neg);
+                if (wide) run_program<false, true>(args, sm, tab, q, qinv_neg, first_step);
+                else run_program<false, false>(args, sm, tab, q, qinv_neg, first_step);
             }
             const uint2 *hp = hm + (int64_t)(k * fx.nd + d) * hstride;
             auto mac1 = [&](uint32_t x, uint32_t h0, uint32_t h1, uint32_t &a0, uint32_t &a1) {

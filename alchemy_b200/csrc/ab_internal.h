@@ -205,6 +205,8 @@ struct AbMxMac {
     int64_t add_ustride;
     const int64_t *add0;         // optional [unit][L][n] added to component 0 (tunnel: the evalLin part)
     int64_t add0_ustride;
+    const uint32_t *bits_lut[AB_MAX_LIMBS];   // per limb: subset-sum tables of the first step for binary digits (null: generic path)
+    int32_t bits_p, bits_h;
     void *acc;                   // scratch of ab_mixed_mac_scratch_words() int64 words (may be null when that is 0)
     int64_t *tbuf;               // optional scratch of [unit][parts][L][n] int64 words (used as uint32: the source residues gathered once per (k, source limb))
     int64_t *out;                // [unit][2][L][n]
@@ -235,6 +237,12 @@ struct ab_plan {
     std::vector<AbMxStep> mx_fwd, mx_inv;
     std::vector<const uint32_t *> mx_tab_fwd, mx_tab_inv;   // per limb, device
     int32_t mx_words_fwd[2] = {0, 0}, mx_words_inv[2] = {0, 0};   // table block size (uint32 words): narrow, wide layout
+    // binary-digit first step (gadget base 2): when the first forward step is the twiddle-free (p-1)-point CRT_p of the last
+    // axis, the step applied to digits in {-1, 0} is a subset sum of matrix columns: per limb two lookup tables
+    // lut[half][row][subset] = -(sum of M[row][c] over the columns c of that half whose bit is set) mod q, half = low / high
+    // ceil(P/2) columns.  mx_bits_p = P (0: not available), mx_bits_h = ceil(P/2); device pointer per limb.
+    int32_t mx_bits_p = 0, mx_bits_h = 0;
+    std::vector<const uint32_t *> mx_bits_lut;
     std::vector<uint8_t> mx_ok;                             // per limb: 0 = not supported, 1 = narrow (q < 2^30), 2 = wide
     // host copies kept for tests / ext construction
     std::vector<int64_t> mhat_inv;        // per limb

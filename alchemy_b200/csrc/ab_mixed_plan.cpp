@@ -221,6 +221,31 @@ void ab_build_mixed(ab_plan *pl) {
         }
     }
     if ((int)recs.size() > AB_MX_MAX_STEPS) return;
+    // subset-sum tables of the first forward step for binary gadget digits (see ab_internal.h): only when that step is one
+    // uniform matrix over contiguous items
+    std::vector<std::vector<uint32_t>> bits_lut;
+    int bits_p = 0, bits_h = 0;
+    if (!recs.empty() && recs[0].step.kind == 0 && recs[0].step.estride == 1 && recs[0].step.row_mode == 0 && recs[0].step.span <= 12 &&
+        recs[0].mats[0].size() == 1) {
+        bits_p = recs[0].step.span; bits_h = (bits_p + 1) / 2;
+        bits_lut.resize(L);
+        for (int l = 0; l < L; ++l) {
+            const uint64_t q = pl->q[l];
+            const auto &M = recs[0].mats[l][0];
+            auto &T = bits_lut[l];
+            T.assign((size_t)2 * bits_p * (1u << bits_h), 0);
+            for (int half = 0; half < 2; ++half)
+                for (int r = 0; r < bits_p; ++r)
+                    for (uint32_t sub = 0; sub < (1u << bits_h); ++sub) {
+                        uint64_t acc = 0;
+                        for (int b = 0; b < bits_h; ++b) {
+                            const int c = half * bits_h + b;
+                            if (((sub >> b) & 1) && c < bits_p) acc = (acc + M[(size_t)r * bits_p + c]) % q;
+                        }
+                        T[((size_t)half * bits_p + r) * (1u << bits_h) + sub] = (uint32_t)((q - acc) % q);
+                    }
+        }
+    }
 
     auto emit = [&](Builder &B, const Pending &rec, bool inverse) {
         AbMxStep s = rec.step;
@@ -281,6 +306,15 @@ void ab_build_mixed(ab_plan *pl) {
     pl->mx_inv = I.steps;
     pl->mx_words_fwd[0] = F.off_n; pl->mx_words_fwd[1] = F.off_w;
     pl->mx_words_inv[0] = I.off_n; pl->mx_words_inv[1] = I.off_w;
+    pl->mx_bits_p = bits_p; pl->mx_bits_h = bits_h;
+    pl->mx_bits_lut.assign(L, nullptr);
+    for (int l = 0; l < L && bits_p; ++l) {
+        uint32_t *dl = nullptr;
+        AB_CHECK_CUDA(cudaMalloc((void **)&dl, bits_lut[l].size() * 4));
+        pl->owned.push_back(dl);
+        AB_CHECK_CUDA(cudaMemcpy(dl, bits_lut[l].data(), bits_lut[l].size() * 4, cudaMemcpyHostToDevice));
+        pl->mx_bits_lut[l] = dl;
+    }
     pl->mx_tab_fwd.assign(L, nullptr);
     pl->mx_tab_inv.assign(L, nullptr);
     for (int l = 0; l < L; ++l) {
