@@ -2,6 +2,8 @@
 ab_tunnel_dev, ab_decompose_dev, ab_rescale_drop_dev): bit-exact against oracle/she_oracle.py, which
 computes the same operations definitionally through the powerful basis (run under gpurun: `pytest -m gpu`).
 Shapes follow the limb schedule of the reference's examples."""
+import os
+
 import numpy as np
 import pytest
 
@@ -205,3 +207,19 @@ def test_empty_batches_and_bad_arguments_of_the_fused_entries():
     assert torch.equal(y, keep)
     with pytest.raises(ab.AlchemyError):
         ab.GT.divGPow(p9, y)
+
+
+@pytest.mark.parametrize("switch", ["AB_NO_MAC=1", "AB_NO_BITS=1", "AB_NO_MULTIDROP=1", "AB_NO_MULKS=1", "AB_MX_MAC_PARTS=5", "AB_MX_T=128", "AB_MX_MAC_T=256"])
+def test_every_kernel_variant_computes_the_same_bits(switch):
+    """the A/B switches of DESIGN.md section 5 select alternative kernels / launch sequences; each must pass the same parity tests
+    (the switches are read once per process, hence the subprocess)"""
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    k, v = switch.split("=")
+    env[k] = v
+    here = os.path.dirname(os.path.abspath(__file__))
+    sel = "mul_keyswitch_pipeline or test_mod_switch or test_tunnel"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_she.py"), "-x", "-q", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
