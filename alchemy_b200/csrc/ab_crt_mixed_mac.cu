@@ -7,7 +7,7 @@ void ab_mx_launch_mac_smem(dim3 grid, int T, size_t smem, cudaStream_t st, const
 
 // out_c = add_c + sum over the parts of a unit of the partial sums (parts > 1 only)
 __global__ void __launch_bounds__(256) k_mac_combine(const __grid_constant__ MxArgs args, const __grid_constant__ AbMxMac mac) {
-    const int n = args.n, L = args.nlimbs, parts = mac.parts;
+    const int n = mac.n_out > 0 ? mac.n_out : args.n, L = args.nlimbs, parts = mac.parts;
     const int64_t per = (int64_t)L * n, total = args.batch * per;
     const uint2 *acc = reinterpret_cast<const uint2 *>(mac.acc);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -70,7 +70,8 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     mac2.bits_p = no_bits ? 0 : p->mx_bits_p; mac2.bits_h = p->mx_bits_h;
     for (int l = 0; l < nlimbs; ++l) mac2.bits_lut[l] = (mac2.bits_p && (size_t)l < p->mx_bits_lut.size()) ? p->mx_bits_lut[l] : nullptr;
     const int parts = mac.parts > 1 ? mac.parts : 1;
-    const bool acc_smem = parts == 1 && mac_acc_in_smem(p, std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]));
+    AB_REQUIRE(mac.n_out == 0 || (mac.rep_idx && (mac.n_out & 1) == 0), AB_ERR_ARG, "fused gadget inner product: replicated mode needs an index table and an even output size");
+    const bool acc_smem = parts == 1 && mac.n_out == 0 && mac_acc_in_smem(p, std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]));
     AB_REQUIRE(acc_smem || mac.acc, AB_ERR_ARG, "fused gadget inner product: scratch missing");
     const size_t smem = mac_smem(p, max_words, acc_smem);
     static const int force_t = getenv("AB_MX_MAC_T") ? atoi(getenv("AB_MX_MAC_T")) : 0;      // experiments only
@@ -81,7 +82,7 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     ab_count_launch();
     ab_check_launch("crt_mixed_mac");
     if (parts > 1) {
-        const int64_t work = units * nlimbs * p->n;
+        const int64_t work = units * nlimbs * (mac.n_out > 0 ? mac.n_out : p->n);
         const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)p->sm_count * 16));
         k_mac_combine<<<g, 256, 0, st>>>(args, mac2);
         ab_count_launch();

@@ -27,8 +27,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
     const int parts = mac.parts > 1 ? mac.parts : 1;
     const int64_t unit = blockIdx.x / parts, slice = blockIdx.x;          // slice = unit * parts + part
     const int part = (int)(blockIdx.x - unit * parts);
+    const int nm = (!ACC_SMEM && mac.n_out > 0) ? mac.n_out : n;       // positions of the inner product (hint, sums, output)
+    const int32_t *rep = (!ACC_SMEM && mac.n_out > 0) ? mac.rep_idx : nullptr;
     uint2 *acc = ACC_SMEM ? reinterpret_cast<uint2 *>(sm + nb)
-                          : reinterpret_cast<uint2 *>(mac.acc) + (slice * args.nlimbs + limb) * (int64_t)n;
+                          : reinterpret_cast<uint2 *>(mac.acc) + (slice * args.nlimbs + limb) * (int64_t)nm;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(args.limb[limb].tab);
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
@@ -37,8 +39,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
     uint32_t *tbuf = (mac.tbuf && fx.gbase != 0) ? reinterpret_cast<uint32_t *>(mac.tbuf) + (slice * args.nlimbs + limb) * (int64_t)nb : nullptr;
     // subset-sum tables apply to base 2 with the digits cut from the gathered residues, on a 16-byte aligned residue buffer
     const uint32_t *bits_lut = (tbuf && fx.gbase == 2 && mac.bits_p > 0 && (n % mac.bits_p) == 0 && ((uintptr_t)sm & 15) == 0) ? mac.bits_lut[limb] : nullptr;
-    const uint2 *hm = reinterpret_cast<const uint2 *>(mac.hm) + (int64_t)limb * n;
-    const int64_t hstride = (int64_t)args.nlimbs * n;
+    const uint2 *hm = reinterpret_cast<const uint2 *>(mac.hm) + (int64_t)limb * nm;
+    const int64_t hstride = (int64_t)args.nlimbs * nm;
     bool first = true;
     const int total_digits = mac.K * fx.nd, per_part = (total_digits + parts - 1) / parts;
     const int kd0 = part * per_part, kd1 = min(total_digits, kd0 + per_part);
@@ -80,10 +82,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
             };
             // four consecutive positions per thread and step: 16-byte loads of the hint pairs, the running sums and the
             // residues; thread t owns the same positions for every digit (the sums need no synchronisation)
-            const int T = blockDim.x, n4 = n >> 2;
+            const int T = blockDim.x, n4 = nm >> 2;
             const uint4 *h4 = reinterpret_cast<const uint4 *>(hp);
             uint4 *a4 = reinterpret_cast<uint4 *>(acc);
             const uint4 *x4 = reinterpret_cast<const uint4 *>(sm);
+            const int4 *r4 = reinterpret_cast<const int4 *>(rep);
             for (int g = threadIdx.x; g < n4; g += T) {
                 const uint4 ha = __ldg(h4 + 2 * g), hb2 = __ldg(h4 + 2 * g + 1);
                 uint4 aa = make_uint4(0, 0, 0, 0), ab2 = aa;
@@ -91,7 +94,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
                     if (ACC_SMEM) { aa = a4[2 * g]; ab2 = a4[2 * g + 1]; }
                     else { aa = __ldcg(a4 + 2 * g); ab2 = __ldcg(a4 + 2 * g + 1); }
                 }
-                const uint4 x = x4[g];
+                uint4 x;
+                if (rep) { const int4 ix = __ldg(r4 + g); x = make_uint4(sm[ix.x], sm[ix.y], sm[ix.z], sm[ix.w]); }
+                else x = x4[g];
                 mac1(x.x, ha.x, ha.y, aa.x, aa.y);
                 mac1(x.y, ha.z, ha.w, aa.z, aa.w);
                 mac1(x.z, hb2.x, hb2.y, ab2.x, ab2.y);
@@ -99,11 +104,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
                 if (ACC_SMEM) { a4[2 * g] = aa; a4[2 * g + 1] = ab2; }
                 else { __stcg(a4 + 2 * g, aa); __stcg(a4 + 2 * g + 1, ab2); }
             }
-            for (int j = 4 * n4 + threadIdx.x; j < n; j += T) {
+            for (int j = 4 * n4 + threadIdx.x; j < nm; j += T) {
                 const uint2 h = __ldg(hp + j);
                 uint2 a = make_uint2(0, 0);
                 if (!first) a = ACC_SMEM ? acc[j] : __ldcg(acc + j);
-                mac1(sm[j], h.x, h.y, a.x, a.y);
+                mac1(sm[rep ? __ldg(rep + j) : j], h.x, h.y, a.x, a.y);
                 if (ACC_SMEM) acc[j] = a;
                 else __stcg(acc + j, a);
             }
@@ -112,15 +117,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
         }
     }
     if (first && !ACC_SMEM) {       // a part that received no digit (parts does not divide the digit count): its partial sum is zero
-        for (int j = threadIdx.x; j < n; j += blockDim.x) __stcg(acc + j, make_uint2(0, 0));
+        for (int j = threadIdx.x; j < nm; j += blockDim.x) __stcg(acc + j, make_uint2(0, 0));
     }
     if (parts == 1) {
         const int64_t per = hstride;
-        int64_t *o0 = mac.out + unit * mac.out_ustride + (int64_t)limb * n, *o1 = o0 + per;
-        const int64_t *a0 = mac.add ? mac.add + unit * mac.add_ustride + (int64_t)limb * n : nullptr;
+        int64_t *o0 = mac.out + unit * mac.out_ustride + (int64_t)limb * nm, *o1 = o0 + per;
+        const int64_t *a0 = mac.add ? mac.add + unit * mac.add_ustride + (int64_t)limb * nm : nullptr;
         const int64_t *a1 = a0 ? a0 + per : nullptr;
-        const int64_t *l0 = mac.add0 ? mac.add0 + unit * mac.add0_ustride + (int64_t)limb * n : nullptr;
-        for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
+        const int64_t *l0 = mac.add0 ? mac.add0 + unit * mac.add0_ustride + (int64_t)limb * nm : nullptr;
+        for (int i = threadIdx.x; i < nm / 2; i += blockDim.x) {
             // positions 2i, 2i+1 were accumulated by other threads of this CTA: the barrier after the last digit orders them
             const uint2 u = ACC_SMEM ? acc[2 * i] : __ldcg(acc + 2 * i), v = ACC_SMEM ? acc[2 * i + 1] : __ldcg(acc + 2 * i + 1);
             uint32_t r00 = u.x, r01 = v.x, r10 = u.y, r11 = v.y;      // r[c][column]

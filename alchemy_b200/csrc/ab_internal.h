@@ -207,6 +207,12 @@ struct AbMxMac {
     int64_t add0_ustride;
     const uint32_t *bits_lut[AB_MAX_LIMBS];   // per limb: subset-sum tables of the first step for binary digits (null: generic path)
     int32_t bits_p, bits_h;
+    // replicated mode (tunnel): the digits live in the SUB-ring O_e' (the plan handed to the kernel, n = phi(e')) and the
+    // inner product runs over the n_out = phi(s') CRT rows of O_s': CRT_s'(embed x) = embedCRT(CRT_e'(x)) is a replication of
+    // the small transform through rep_idx[j] = CRT row of O_e' below row j of O_s' (Lol `embedCRT`), so every digit
+    // transform is phi(s') / phi(e') times smaller.  n_out = 0: plain mode (hint, sums and output over the plan's own n).
+    const int32_t *rep_idx;
+    int32_t n_out, pad3;
     void *acc;                   // scratch of ab_mixed_mac_scratch_words() int64 words (may be null when that is 0)
     int64_t *tbuf;               // optional scratch of [unit][parts][L][n] int64 words (used as uint32: the source residues gathered once per (k, source limb))
     int64_t *out;                // [unit][2][L][n]

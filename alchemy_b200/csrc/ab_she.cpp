@@ -8,6 +8,7 @@
 // chunks of that size).  All polynomials are in the CRT basis, PLANAR layout: c[b][i][l][j].
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "ab_internal.h"
 #include "ab_kernels.h"
@@ -267,6 +268,10 @@ struct ab_tunnel {
     int32_t *d_pow = nullptr;      // [K][n_s] index into [n_r] of the powerful-basis source, -1 = zero
     int32_t *d_dec = nullptr;      // same for the decoding basis
     int8_t *d_dec_sgn = nullptr;   // [K][n_s]
+    // sub-ring route for the c1 part: CRT_s'(embed x) = embedCRT(CRT_e'(x)), so the gadget digit transforms run in O_e' (a plan
+    // with CRT tables for e' over the moduli of s', root omega_s'^(s'/e')) and are replicated through es_crt->d_base_crt
+    ab_plan *ecrt = nullptr;
+    ab_ext *es_crt = nullptr;
 };
 
 extern "C" int ab_tunnel_create(ab_tunnel **out, const ab_plan *plan_r, const ab_plan *plan_e, const ab_plan *plan_s) {
@@ -303,6 +308,16 @@ extern "C" int ab_tunnel_create(ab_tunnel **out, const ab_plan *plan_r, const ab
         AB_CHECK_CUDA(cudaMemcpy(t->d_pow, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice));
         AB_CHECK_CUDA(cudaMemcpy(t->d_dec, td.data(), td.size() * 4, cudaMemcpyHostToDevice));
         AB_CHECK_CUDA(cudaMemcpy(t->d_dec_sgn, ts.data(), ts.size(), cudaMemcpyHostToDevice));
+        // CRT plan of e' over the moduli of s' (e' | s' | q - 1), same root family; optional: without it the digits run in O_s'
+        if (plan_e->m > 2 && K >= 1 && ns > ne) {
+            std::vector<ab_prime_exp> pe;
+            for (const AbAxis &ax : plan_e->axes) pe.push_back(ab_prime_exp{ax.p, ax.e});
+            std::vector<int64_t> roots;
+            for (int l = 0; l < plan_s->L; ++l)
+                roots.push_back((int64_t)abh::powmod((uint64_t)plan_s->root[l], (uint64_t)(plan_s->m / plan_e->m), (uint64_t)plan_s->q[l]));
+            if (ab_plan_create(&t->ecrt, pe.data(), (int32_t)pe.size(), plan_s->q.data(), plan_s->L, roots.data()) != AB_OK) t->ecrt = nullptr;
+            else if (ab_ext_create(&t->es_crt, t->ecrt, plan_s) != AB_OK) { ab_plan_destroy(t->ecrt); t->ecrt = nullptr; t->es_crt = nullptr; }
+        }
         *out = t;
     });
     if (rc != AB_OK && t) ab_tunnel_destroy(t);
@@ -312,6 +327,8 @@ extern "C" void ab_tunnel_destroy(ab_tunnel *t) {
     if (!t) return;
     ab_ext_destroy(t->er);
     ab_ext_destroy(t->es);
+    if (t->es_crt) ab_ext_destroy(t->es_crt);
+    if (t->ecrt) ab_plan_destroy(t->ecrt);
     cudaFree(t->d_pow);
     cudaFree(t->d_dec);
     cudaFree(t->d_dec_sgn);
@@ -399,11 +416,20 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                 AbMxFused fx{};
                 fx.load_mode = AB_MX_LOAD_DIGITS;
                 fill_digits(ps, nlimbs, base, fx, false);
-                fx.src = cin + per_r; fx.src_ustride = 2 * per_r; fx.n_src = (int32_t)nr; fx.gather = t->d_pow; fx.gK = (int32_t)K;
+                fx.src = cin + per_r; fx.src_ustride = 2 * per_r; fx.n_src = (int32_t)nr; fx.gK = (int32_t)K;
                 AbMxMac mac{};
                 mac.hm = hm; mac.K = (int32_t)K; mac.add0 = lin; mac.add0_ustride = per_s; mac.acc = accs; mac.tbuf = tb; mac.parts = parts;
                 mac.out = out2_s + b0 * 2 * per_s; mac.out_ustride = 2 * per_s;
-                ab_launch_crt_mixed_mac(ps, B, nlimbs, fx, mac, st);
+                static const bool no_sub = getenv("AB_NO_SUBRING") && atoi(getenv("AB_NO_SUBRING")) != 0;      // A/B measurements only
+                if (!no_sub && t->ecrt && (ns & 3) == 0 && !ab_pow2_supported(t->ecrt) && ab_mixed_mac_supported(t->ecrt, nlimbs)) {
+                    // digits of embed(coeffs_k(c1)) = embed(digits of coeffs_k(c1)): transform them in O_e' and replicate (embedCRT)
+                    fx.gather = t->er->d_coeff;
+                    mac.rep_idx = t->es_crt->d_base_crt; mac.n_out = (int32_t)ns;
+                    ab_launch_crt_mixed_mac(t->ecrt, B, nlimbs, fx, mac, st);
+                } else {
+                    fx.gather = t->d_pow;
+                    ab_launch_crt_mixed_mac(ps, B, nlimbs, fx, mac, st);
+                }
             }
             return;
         }
