@@ -73,7 +73,14 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     AB_REQUIRE(mac.n_out == 0 || (mac.rep_idx && (mac.n_out & 1) == 0), AB_ERR_ARG, "fused gadget inner product: replicated mode needs an index table and an even output size");
     const bool acc_smem = parts == 1 && mac.n_out == 0 && mac_acc_in_smem(p, std::max(p->mx_words_fwd[0], p->mx_words_fwd[1]));
     AB_REQUIRE(acc_smem || mac.acc, AB_ERR_ARG, "fused gadget inner product: scratch missing");
-    const size_t smem = mac_smem(p, max_words, acc_smem);
+    // replicated mode: the transforms are small, so several of them fit shared memory side by side (about 40 KB of residues keeps
+    // four to five CTAs per SM)
+    const size_t nbw = (((size_t)p->n + 3) & ~(size_t)3) * sizeof(uint32_t);
+    static const int force_g = getenv("AB_MX_MAC_GROUP") ? atoi(getenv("AB_MX_MAC_GROUP")) : 0;      // experiments only
+    int group = 1;
+    if (mac.n_out > 0 && !acc_smem) group = force_g > 0 ? std::min(force_g, 8) : (int)std::max<size_t>(1, std::min<size_t>(8, (40 * 1024) / nbw));
+    mac2.group = group;
+    const size_t smem = mac_smem(p, max_words, acc_smem) + (size_t)(group - 1) * nbw;
     static const int force_t = getenv("AB_MX_MAC_T") ? atoi(getenv("AB_MX_MAC_T")) : 0;      // experiments only
     const int T = force_t ? force_t : pick_threads(p->mx_fwd, (int)p->n, smem);
     const dim3 grid((unsigned)(units * parts), (unsigned)nlimbs);

@@ -44,77 +44,109 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
     bool first = true;
     const int total_digits = mac.K * fx.nd, per_part = (total_digits + parts - 1) / parts;
     const int kd0 = part * per_part, kd1 = min(total_digits, kd0 + per_part);
-    {
-        for (int kd = kd0; kd < kd1; ++kd) {
+    // G digit transforms are kept side by side in shared memory (replicated mode: they are small) and ONE inner-product pass
+    // consumes all of them: the running sums, the index table and the reductions are touched once per G digits, and the G
+    // products per output are accumulated exactly in 64 bits (narrow moduli: terms below 2^60, G <= 8) before one Montgomery step
+    const int G = ACC_SMEM ? 1 : max(1, min(mac.group, 8));
+    const int lazy_terms = wide ? 1 : 8;
+    for (int kdg = kd0; kdg < kd1; kdg += G) {
+        const int gcount = min(G, kd1 - kdg);
+        for (int gi = 0; gi < gcount; ++gi) {
+            const int kd = kdg + gi;
             const int k = kd / fx.nd, d = kd - k * fx.nd;
+            uint32_t *buf = sm + gi * nb;
             const bool triv = mx_digit_is_trivial(fx, d, limb);
             int first_step = 0;
             if (triv) {
                 const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
-                uint2 *dst = reinterpret_cast<uint2 *>(sm);
+                uint2 *dst = reinterpret_cast<uint2 *>(buf);
                 for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
                     const int4 v = __ldcs(src + i);
                     dst[i] = make_uint2((uint32_t)v.x, (uint32_t)v.z);
                 }
             } else if (tbuf) {
                 if (kd == kd0 || d == 0 || fx.dig[d].limb != fx.dig[d - 1].limb) {
+                    __syncthreads();      // every earlier reader of t is done
                     mx_gather_centered(fx, d, unit, k, n, tbuf);
                     __syncthreads();      // the digit pass reads t with a different thread-to-position map
                 }
                 // binary gadget: digit and first transform step in one pass (subset-sum tables), except for the last digit
-                if (bits_lut && !fx.dig[d].last) first_step = mx_bits_dispatch(mac.bits_p, fx, d, n, q, tbuf, bits_lut, sm) ? 1 : 0;
-                if (!first_step) mx_digit_from_t(fx, d, n, q, tbuf, sm);
+                if (bits_lut && !fx.dig[d].last) first_step = mx_bits_dispatch(mac.bits_p, fx, d, n, q, tbuf, bits_lut, buf) ? 1 : 0;
+                if (!first_step) mx_digit_from_t(fx, d, n, q, tbuf, buf);
             } else {
-                mx_load_digit(fx, d, unit, k, n, q, sm);
+                mx_load_digit(fx, d, unit, k, n, q, buf);
             }
             __syncthreads();
             if (!triv) {
-                if (wide) run_program<false, true>(args, sm, tab, q, qinv_neg, first_step);
-                else run_program<false, false>(args, sm, tab, q, qinv_neg, first_step);
+                if (wide) run_program<false, true>(args, buf, tab, q, qinv_neg, first_step);
+                else run_program<false, false>(args, buf, tab, q, qinv_neg, first_step);
             }
-            const uint2 *hp = hm + (int64_t)(k * fx.nd + d) * hstride;
-            auto mac1 = [&](uint32_t x, uint32_t h0, uint32_t h1, uint32_t &a0, uint32_t &a1) {
-                const uint64_t t0 = (uint64_t)x * h0, t1 = (uint64_t)x * h1;
-                const uint32_t r0 = (uint32_t)((t0 + (uint64_t)((uint32_t)t0 * qinv_neg) * q) >> 32);
-                const uint32_t r1 = (uint32_t)((t1 + (uint64_t)((uint32_t)t1 * qinv_neg) * q) >> 32);
-                a0 = ab_addmod(ab_csub(r0, q), a0, q);
-                a1 = ab_addmod(ab_csub(r1, q), a1, q);
-            };
-            // four consecutive positions per thread and step: 16-byte loads of the hint pairs, the running sums and the
-            // residues; thread t owns the same positions for every digit (the sums need no synchronisation)
-            const int T = blockDim.x, n4 = nm >> 2;
-            const uint4 *h4 = reinterpret_cast<const uint4 *>(hp);
-            uint4 *a4 = reinterpret_cast<uint4 *>(acc);
-            const uint4 *x4 = reinterpret_cast<const uint4 *>(sm);
-            const int4 *r4 = reinterpret_cast<const int4 *>(rep);
-            for (int g = threadIdx.x; g < n4; g += T) {
-                const uint4 ha = __ldg(h4 + 2 * g), hb2 = __ldg(h4 + 2 * g + 1);
-                uint4 aa = make_uint4(0, 0, 0, 0), ab2 = aa;
-                if (!first) {
-                    if (ACC_SMEM) { aa = a4[2 * g]; ab2 = a4[2 * g + 1]; }
-                    else { aa = __ldcg(a4 + 2 * g); ab2 = __ldcg(a4 + 2 * g + 1); }
-                }
-                uint4 x;
-                if (rep) { const int4 ix = __ldg(r4 + g); x = make_uint4(sm[ix.x], sm[ix.y], sm[ix.z], sm[ix.w]); }
-                else x = x4[g];
-                mac1(x.x, ha.x, ha.y, aa.x, aa.y);
-                mac1(x.y, ha.z, ha.w, aa.z, aa.w);
-                mac1(x.z, hb2.x, hb2.y, ab2.x, ab2.y);
-                mac1(x.w, hb2.z, hb2.w, ab2.z, ab2.w);
-                if (ACC_SMEM) { a4[2 * g] = aa; a4[2 * g + 1] = ab2; }
-                else { __stcg(a4 + 2 * g, aa); __stcg(a4 + 2 * g + 1, ab2); }
-            }
-            for (int j = 4 * n4 + threadIdx.x; j < nm; j += T) {
-                const uint2 h = __ldg(hp + j);
-                uint2 a = make_uint2(0, 0);
-                if (!first) a = ACC_SMEM ? acc[j] : __ldcg(acc + j);
-                mac1(sm[rep ? __ldg(rep + j) : j], h.x, h.y, a.x, a.y);
-                if (ACC_SMEM) acc[j] = a;
-                else __stcg(acc + j, a);
-            }
-            first = false;
-            __syncthreads();       // the next digit overwrites sm
         }
+        const uint2 *hp = hm + (int64_t)kdg * hstride;            // hint of digit kdg + gi at hp + gi * hstride
+        auto fold = [&](uint64_t &s, uint32_t &a, bool many) {    // a += REDC(s), s = 0; a single term reduces to below 2q
+            uint32_t t = (uint32_t)((s + (uint64_t)((uint32_t)s * qinv_neg) * q) >> 32);
+            if (many) t = ab_csub(t, 2 * q);
+            a = ab_addmod(ab_csub(t, q), a, q);
+            s = 0;
+        };
+        // four consecutive positions per thread and step: 16-byte loads of the hint pairs, the running sums and the
+        // residues; thread t owns the same positions for every digit (the sums need no synchronisation)
+        const int T = blockDim.x, n4 = nm >> 2;
+        uint4 *a4 = reinterpret_cast<uint4 *>(acc);
+        const int4 *r4 = reinterpret_cast<const int4 *>(rep);
+        for (int g = threadIdx.x; g < n4; g += T) {
+            uint4 aa = make_uint4(0, 0, 0, 0), ab2 = aa;
+            if (!first) {
+                if (ACC_SMEM) { aa = a4[2 * g]; ab2 = a4[2 * g + 1]; }
+                else { aa = __ldcg(a4 + 2 * g); ab2 = __ldcg(a4 + 2 * g + 1); }
+            }
+            int4 ix = make_int4(4 * g, 4 * g + 1, 4 * g + 2, 4 * g + 3);
+            if (rep) ix = __ldg(r4 + g);
+            uint64_t s00 = 0, s01 = 0, s10 = 0, s11 = 0, s20 = 0, s21 = 0, s30 = 0, s31 = 0;      // [position][component]
+            auto term = [&](int gi) {
+                const uint4 *h4 = reinterpret_cast<const uint4 *>(hp + (int64_t)gi * hstride);
+                const uint4 ha = __ldg(h4 + 2 * g), hb2 = __ldg(h4 + 2 * g + 1);
+                const uint32_t *buf = sm + gi * nb;
+                uint4 x;
+                if (rep) x = make_uint4(buf[ix.x], buf[ix.y], buf[ix.z], buf[ix.w]);
+                else x = reinterpret_cast<const uint4 *>(buf)[g];
+                s00 += (uint64_t)x.x * ha.x; s01 += (uint64_t)x.x * ha.y;
+                s10 += (uint64_t)x.y * ha.z; s11 += (uint64_t)x.y * ha.w;
+                s20 += (uint64_t)x.z * hb2.x; s21 += (uint64_t)x.z * hb2.y;
+                s30 += (uint64_t)x.w * hb2.z; s31 += (uint64_t)x.w * hb2.w;
+            };
+            auto fold_all = [&](bool many) {
+                fold(s00, aa.x, many); fold(s01, aa.y, many); fold(s10, aa.z, many); fold(s11, aa.w, many);
+                fold(s20, ab2.x, many); fold(s21, ab2.y, many); fold(s30, ab2.z, many); fold(s31, ab2.w, many);
+            };
+            if (gcount == 1) {          // the common plain case: no loop, constant offsets
+                term(0);
+                fold_all(false);
+            } else {
+                int terms = 0;
+                for (int gi = 0; gi < gcount; ++gi) {
+                    term(gi);
+                    if (++terms == lazy_terms || gi + 1 == gcount) { fold_all(terms > 1); terms = 0; }
+                }
+            }
+            if (ACC_SMEM) { a4[2 * g] = aa; a4[2 * g + 1] = ab2; }
+            else { __stcg(a4 + 2 * g, aa); __stcg(a4 + 2 * g + 1, ab2); }
+        }
+        for (int j = 4 * n4 + threadIdx.x; j < nm; j += T) {
+            uint2 a = make_uint2(0, 0);
+            if (!first) a = ACC_SMEM ? acc[j] : __ldcg(acc + j);
+            const int jx = rep ? __ldg(rep + j) : j;
+            for (int gi = 0; gi < gcount; ++gi) {
+                const uint2 h = __ldg(hp + (int64_t)gi * hstride + j);
+                const uint32_t x = sm[gi * nb + jx];
+                uint64_t s0 = (uint64_t)x * h.x, s1 = (uint64_t)x * h.y;
+                fold(s0, a.x, false); fold(s1, a.y, false);
+            }
+            if (ACC_SMEM) acc[j] = a;
+            else __stcg(acc + j, a);
+        }
+        first = false;
+        __syncthreads();       // the next group overwrites the residue buffers
     }
     if (first && !ACC_SMEM) {       // a part that received no digit (parts does not divide the digit count): its partial sum is zero
         for (int j = threadIdx.x; j < nm; j += blockDim.x) __stcg(acc + j, make_uint2(0, 0));

@@ -212,7 +212,7 @@ struct AbMxMac {
     // the small transform through rep_idx[j] = CRT row of O_e' below row j of O_s' (Lol `embedCRT`), so every digit
     // transform is phi(s') / phi(e') times smaller.  n_out = 0: plain mode (hint, sums and output over the plan's own n).
     const int32_t *rep_idx;
-    int32_t n_out, pad3;
+    int32_t n_out, group;        // group: digit transforms held in shared memory per inner-product pass (1..8; filled in by the launcher)
     void *acc;                   // scratch of ab_mixed_mac_scratch_words() int64 words (may be null when that is 0)
     int64_t *tbuf;               // optional scratch of [unit][parts][L][n] int64 words (used as uint32: the source residues gathered once per (k, source limb))
     int64_t *out;                // [unit][2][L][n]
