@@ -62,6 +62,21 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
             for (int i = k - 2; i >= 0; --i) acc = ab_addmod(ab_mulmod(acc, qmod[i], q, mu), mx_reduce_signed(r[i], q), q);
             sm[j] = acc;
         }
+    } else if (args.fx.load_mode == AB_MX_LOAD_GATHER) {
+        const AbMxFused &fx = args.fx;
+        const int64_t su = blockIdx.x / fx.gK;
+        const int32_t *__restrict__ gt = fx.gather + (int64_t)(blockIdx.x % fx.gK) * n;
+        const int64_t *__restrict__ src = fx.src + su * fx.src_ustride + (int64_t)limb * fx.n_src;
+        for (int j0 = threadIdx.x; j0 < n; j0 += 4 * blockDim.x) {
+            int32_t g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = j0 + u * blockDim.x; g[u] = j < n ? __ldg(gt + j) : -1; }
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = g[u] >= 0 ? (uint32_t)__ldg(src + g[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = j0 + u * blockDim.x; if (j < n) sm[j] = v[u]; }
+        }
     } else if (args.fx.load_mode == AB_MX_LOAD_SRC) {
         // out of place: read the transform from another planar buffer (e.g. c2 of a degree-2 ciphertext)
         const int4 *src = reinterpret_cast<const int4 *>(args.fx.src + blockIdx.x * args.fx.src_ustride + (int64_t)(args.fx.src_limb0 + limb) * n);

@@ -646,25 +646,32 @@ void ab_launch_hint_ip_m(const ab_plan *p, int64_t *out, int64_t out_bstride, co
 }
 
 // acc[b][l][j] (+)= sum_k x[b][k][l][j] * f[k][l][j]      (evalLin of the tunnel's linear function)
-__global__ void __launch_bounds__(256) k_lin_ip(const IpArgs a, int64_t *__restrict__ out, const int64_t *__restrict__ x, const int64_t *__restrict__ f) {
-    const int64_t per = (int64_t)a.nlimbs * a.n, total = a.batch * per;
+// idx != nullptr: x lives in a sub-ring with n_in rows per limb and is replicated through idx (embedCRT): x[b][k][l][idx[j]]
+__global__ void __launch_bounds__(256) k_lin_ip(const IpArgs a, int64_t *__restrict__ out, const int64_t *__restrict__ x, const int64_t *__restrict__ f,
+                                                const int32_t *__restrict__ idx, int64_t n_in) {
+    const int64_t per = (int64_t)a.nlimbs * a.n, total = a.batch * per, per_in = idx ? (int64_t)a.nlimbs * n_in : per;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = i / per, r = i % per;
         const int l = (int)(r / a.n);
         const uint32_t q = a.limb[l].q;
+        const int64_t rin = idx ? (int64_t)l * n_in + __ldg(idx + (r - (int64_t)l * a.n)) : r;
         uint32_t s = 0;
         for (int k = 0; k < a.ndig; ++k)
-            s = ab_addmod(s, ab_mulmod((uint32_t)x[b * a.dig_bstride + k * per + r], (uint32_t)__ldg(f + k * per + r), q, a.limb[l].mu), q);
+            s = ab_addmod(s, ab_mulmod((uint32_t)x[b * a.dig_bstride + k * per_in + rin], (uint32_t)__ldg(f + k * per + r), q, a.limb[l].mu), q);
         out[b * a.out_bstride + r] = (int64_t)s;
     }
 }
 void ab_launch_lin_ip(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *x, int64_t x_bstride, const int64_t *f,
                       int64_t batch, int32_t nlimbs, int32_t nk, cudaStream_t st) {
+    ab_launch_lin_ip_rep(p, out, out_bstride, x, x_bstride, f, nullptr, 0, batch, nlimbs, nk, st);
+}
+void ab_launch_lin_ip_rep(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *x, int64_t x_bstride, const int64_t *f,
+                          const int32_t *idx, int64_t n_in, int64_t batch, int32_t nlimbs, int32_t nk, cudaStream_t st) {
     if (batch == 0) return;
     IpArgs a{};
     a.nlimbs = nlimbs; a.ndig = nk; a.n = p->n; a.batch = batch; a.dig_bstride = x_bstride; a.out_bstride = out_bstride;
     for (int l = 0; l < nlimbs; ++l) { a.limb[l].q = p->limb[l].q; a.limb[l].mu = p->limb[l].mu; }
-    k_lin_ip<<<grid_for(batch * nlimbs * p->n, 256, p->sm_count), 256, 0, st>>>(a, out, x, f);
+    k_lin_ip<<<grid_for(batch * nlimbs * p->n, 256, p->sm_count), 256, 0, st>>>(a, out, x, f, idx, n_in);
     ab_count_launch();
     ab_check_launch("lin_ip");
 }

@@ -153,7 +153,7 @@ struct AbMxStep {
 #define AB_MX_MAX_STEPS 24
 
 // fused load / store of the mixed-radix CRT kernel (key switch, tunnel, modSwitch; ab_she.cpp)
-enum { AB_MX_LOAD_PLAIN = 0, AB_MX_LOAD_DIGITS = 1, AB_MX_LOAD_SRC = 2, AB_MX_LOAD_GARNER = 3 };
+enum { AB_MX_LOAD_PLAIN = 0, AB_MX_LOAD_DIGITS = 1, AB_MX_LOAD_SRC = 2, AB_MX_LOAD_GARNER = 3, AB_MX_LOAD_GATHER = 4 };
 #define AB_MX_MAX_DROP 4
 enum { AB_MX_STORE_PLAIN = 0, AB_MX_STORE_SUBSCALE = 1 };
 #define AB_MX_MAX_DIGITS 64
@@ -161,6 +161,7 @@ struct AbMxFused {
     int32_t load_mode, store_mode;
     // AB_MX_LOAD_DIGITS: transform (unit * nd + d, limb l') = CRT of digit d of src[unit / gK] reduced mod q_l'
     // AB_MX_LOAD_SRC:    transform (unit, limb) read from src + unit * src_ustride + (src_limb0 + limb) * n
+    // AB_MX_LOAD_GATHER: transform (unit, limb)[j] = src[unit / gK][limb][gather[unit % gK][j]]  (coeffs of the tunnel's c0 part; -1 = zero)
     int32_t nd, gbase;               // gbase 0 = TrivGad
     const int64_t *src;              // powerful basis, planar [unit][limb][n_src]
     int64_t src_ustride;

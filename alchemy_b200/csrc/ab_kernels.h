@@ -25,6 +25,9 @@ void ab_launch_hint_ip_m(const ab_plan *p, int64_t *out, int64_t out_bstride, co
                          const int64_t *add, int64_t add_bstride, int64_t batch, int32_t nlimbs, int32_t ndig, cudaStream_t st);
 void ab_launch_lin_ip(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *x, int64_t x_bstride, const int64_t *f,
                       int64_t batch, int32_t nlimbs, int32_t nk, cudaStream_t st);
+// the same with x in a sub-ring (n_in rows per limb), replicated through idx[j] (embedCRT)
+void ab_launch_lin_ip_rep(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *x, int64_t x_bstride, const int64_t *f,
+                          const int32_t *idx, int64_t n_in, int64_t batch, int32_t nlimbs, int32_t nk, cudaStream_t st);
 void ab_launch_copy_rows(int64_t *out, int64_t ob, const int64_t *in, int64_t ib, int64_t len, int64_t batch, cudaStream_t st);
 void ab_launch_rescale_up(const ab_plan *p, int64_t *out, int64_t ob, const int64_t *in, int64_t ib, int64_t batch, int32_t nfrom, int32_t nto, cudaStream_t st);
 

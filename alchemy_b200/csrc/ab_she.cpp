@@ -368,7 +368,7 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
         AB_REQUIRE(nd > 0, AB_ERR_ARG, "bad gadget base");
         for (int l = 0; l < nlimbs; ++l) AB_REQUIRE(pr->q[l] == ps->q[l], AB_ERR_ARG, "r' and s' plans must share their moduli");
         cudaStream_t st = (cudaStream_t)stream;
-        const int64_t nr = pr->n, ns = ps->n, K = t->K;
+        const int64_t nr = pr->n, ns = ps->n, K = t->K, ne = t->e->n;
         const int64_t per_r = (int64_t)nlimbs * nr, per_s = (int64_t)nlimbs * ns;
         const int64_t chunk = chunk_of(batch, tn_item_words(t, nlimbs, nd) * 8);
         int64_t *hm = (int64_t *)work;               // prepared hint: [K][nd][2][L][n_s] uint2
@@ -386,6 +386,9 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                 int64_t *accs = lin + B * per_s;         // [B][parts][L][n_s] running sums of the fused inner product
                 int64_t *tb = accs + B * parts * per_s;  // [B][parts][L][n_s] centred source + H of the current (k, source limb)
                 const int64_t *inb = in2_r + b0 * 2 * per_r;
+                static const bool no_sub = getenv("AB_NO_SUBRING") && atoi(getenv("AB_NO_SUBRING")) != 0;      // A/B measurements only
+                const bool sub_ok = !no_sub && t->ecrt && (ns & 3) == 0 && !ab_pow2_supported(t->ecrt) && ab_mixed_mac_supported(t->ecrt, nlimbs);
+                bool fused_c0 = false;
                 if (fused_ok(pr, nlimbs, inb, cin) && ((2 * per_r * 8) % 16) == 0) {
                     // c0 straight to the decoding basis (crtInv with L^-1 folded in), c1 to the powerful basis: two out-of-place
                     // launches, no copies, no separate L / L^-1 passes; L is folded into the load phase of the forward CRT of the parts
@@ -397,10 +400,20 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                     // c1 lands in the second half of every cin row so that the digit source below keeps its layout
                     f1.dst_ustride = 2 * per_r;
                     ab_launch_crt_mixed_fused(pr, AbView{cin + per_r, B, 0, nlimbs, AB_LAYOUT_PLANAR}, true, &f1, st);
-                    ab_launch_tunnel_gather(ps, p0, c0d, per_r, nr, t->d_dec, t->d_dec_sgn, B, K, nlimbs, st);
-                    AbMxFused fl{};
-                    fl.pre_l = 1;
-                    ab_launch_crt_mixed_fused(ps, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, &fl, st);
+                    if (sub_ok) {
+                        // the E'-coefficients of c0 stay in O_e': gathered in the load phase, decoding -> powerful (L) and CRT_e' in one
+                        // launch; evalLin reads them through the embedCRT index (CRT_s'(embed x) = replicate(CRT_e'(x)))
+                        AbMxFused fg{};
+                        fg.load_mode = AB_MX_LOAD_GATHER; fg.src = c0d; fg.src_ustride = per_r; fg.n_src = (int32_t)nr;
+                        fg.gather = t->er->d_coeff; fg.gK = (int32_t)K; fg.pre_l = 1;
+                        ab_launch_crt_mixed_fused(t->ecrt, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, &fg, st);
+                    } else {
+                        ab_launch_tunnel_gather(ps, p0, c0d, per_r, nr, t->d_dec, t->d_dec_sgn, B, K, nlimbs, st);
+                        AbMxFused fl{};
+                        fl.pre_l = 1;
+                        ab_launch_crt_mixed_fused(ps, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, &fl, st);
+                    }
+                    fused_c0 = true;
                 } else {
                     ab_launch_copy_rows(cin, 2 * per_r, inb, 2 * per_r, 2 * per_r, B, st);
                     ab_crt_dispatch(pr, AbView{cin, B * 2, 0, nlimbs, AB_LAYOUT_PLANAR}, true, st);
@@ -410,7 +423,8 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                     ab_launch_prime_op(ps, AB_PR_L, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, st);
                     ab_crt_dispatch(ps, AbView{p0, B * K, 0, nlimbs, AB_LAYOUT_PLANAR}, false, st);
                 }
-                ab_launch_lin_ip(ps, lin, per_s, p0, K * per_s, flin, B, nlimbs, (int32_t)K, st);
+                if (fused_c0 && sub_ok) ab_launch_lin_ip_rep(ps, lin, per_s, p0, K * (int64_t)nlimbs * ne, flin, t->es_crt->d_base_crt, ne, B, nlimbs, (int32_t)K, st);
+                else ab_launch_lin_ip(ps, lin, per_s, p0, K * per_s, flin, B, nlimbs, (int32_t)K, st);
                 // c1: gather (coeffs . embed), gadget digit, reduction, forward CRT of O_s' and the inner product with
                 // the hint, all inside one kernel; the evalLin part of c0 is added on the way out
                 AbMxFused fx{};
@@ -420,8 +434,7 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                 AbMxMac mac{};
                 mac.hm = hm; mac.K = (int32_t)K; mac.add0 = lin; mac.add0_ustride = per_s; mac.acc = accs; mac.tbuf = tb; mac.parts = parts;
                 mac.out = out2_s + b0 * 2 * per_s; mac.out_ustride = 2 * per_s;
-                static const bool no_sub = getenv("AB_NO_SUBRING") && atoi(getenv("AB_NO_SUBRING")) != 0;      // A/B measurements only
-                if (!no_sub && t->ecrt && (ns & 3) == 0 && !ab_pow2_supported(t->ecrt) && ab_mixed_mac_supported(t->ecrt, nlimbs)) {
+                if (sub_ok) {
                     // digits of embed(coeffs_k(c1)) = embed(digits of coeffs_k(c1)): transform them in O_e' and replicate (embedCRT)
                     fx.gather = t->er->d_coeff;
                     mac.rep_idx = t->es_crt->d_base_crt; mac.n_out = (int32_t)ns;

@@ -209,7 +209,8 @@ def test_empty_batches_and_bad_arguments_of_the_fused_entries():
         ab.GT.divGPow(p9, y)
 
 
-@pytest.mark.parametrize("switch", ["AB_NO_MAC=1", "AB_NO_BITS=1", "AB_NO_MULTIDROP=1", "AB_NO_MULKS=1", "AB_MX_MAC_PARTS=5", "AB_MX_T=128", "AB_MX_MAC_T=256"])
+@pytest.mark.parametrize("switch", ["AB_NO_MAC=1", "AB_NO_BITS=1", "AB_NO_MULTIDROP=1", "AB_NO_MULKS=1", "AB_MX_MAC_PARTS=5", "AB_MX_T=128", "AB_MX_MAC_T=256",
+                                    "AB_NO_SUBRING=1", "AB_MX_MAC_GROUP=1", "AB_MX_MAC_GROUP=3"])
 def test_every_kernel_variant_computes_the_same_bits(switch):
     """the A/B switches of DESIGN.md section 5 select alternative kernels / launch sequences; each must pass the same parity tests
     (the switches are read once per process, hence the subprocess)"""
