@@ -103,13 +103,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
             int4 ix = make_int4(4 * g, 4 * g + 1, 4 * g + 2, 4 * g + 3);
             if (rep) ix = __ldg(r4 + g);
             uint64_t s00 = 0, s01 = 0, s10 = 0, s11 = 0, s20 = 0, s21 = 0, s30 = 0, s31 = 0;      // [position][component]
-            auto term = [&](int gi) {
-                const uint4 *h4 = reinterpret_cast<const uint4 *>(hp + (int64_t)gi * hstride);
-                const uint4 ha = __ldg(h4 + 2 * g), hb2 = __ldg(h4 + 2 * g + 1);
-                const uint32_t *buf = sm + gi * nb;
+            // running pointers instead of index arithmetic per term: the hint pair of this group in digit gi, and the residues
+            const char *hb = reinterpret_cast<const char *>(hp) + (size_t)g * 32;
+            const size_t hstep = (size_t)hstride * sizeof(uint2);
+            const uint32_t *b0 = sm + (rep ? ix.x : 4 * g), *b1 = sm + ix.y, *b2 = sm + ix.z, *b3 = sm + ix.w;
+            auto term = [&](int) {
+                const uint4 ha = __ldg(reinterpret_cast<const uint4 *>(hb)), hb2 = __ldg(reinterpret_cast<const uint4 *>(hb + 16));
                 uint4 x;
-                if (rep) x = make_uint4(buf[ix.x], buf[ix.y], buf[ix.z], buf[ix.w]);
-                else x = reinterpret_cast<const uint4 *>(buf)[g];
+                if (rep) x = make_uint4(*b0, *b1, *b2, *b3);
+                else x = *reinterpret_cast<const uint4 *>(b0);
+                hb += hstep; b0 += nb; b1 += nb; b2 += nb; b3 += nb;
                 s00 += (uint64_t)x.x * ha.x; s01 += (uint64_t)x.x * ha.y;
                 s10 += (uint64_t)x.y * ha.z; s11 += (uint64_t)x.y * ha.w;
                 s20 += (uint64_t)x.z * hb2.x; s21 += (uint64_t)x.z * hb2.y;
