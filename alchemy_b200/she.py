@@ -31,6 +31,8 @@ def modSwitch(plan: Plan, c, to_limbs):
     """rescaleCyc on every coefficient: [B,P,from,n] -> [B,P,to,n] over the leading moduli of the plan"""
     B, P, frm, n = c.shape
     assert n == plan.n
+    if to_limbs == frm:
+        return c          # Lol's RescaleCyc instance for equal moduli is the identity (SURVEY Appendix A); callers never mutate ciphertexts
     out = torch.empty((B, P, to_limbs, n), dtype=torch.int64, device=c.device)
     nbytes = lib().ab_mod_switch_work_bytes(plan.h, B, P, frm, to_limbs)
     assert nbytes >= 0
