@@ -161,7 +161,9 @@ int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int64_t *a2, co
  *   c0' = sum_k embed(coeffsDec(c0)_k) * flin_k            (evalLin of the E'-linear function)
  *   (c0'',c1'') = sum_k sum_d reduce(decompose(embed(coeffsPow(c1)_k)))_d * hint_{k,d}
  * `flin`: [rel_dim][nlimbs][n_s] CRT basis of O_s';  `hint`: [rel_dim][gadget_len][2][nlimbs][n_s].
- * Input (c0,c1) over O_r' in the CRT basis; output (c0,c1) over O_s' in the CRT basis. */
+ * Input (c0,c1) over O_r' in the CRT basis; output (c0,c1) over O_s' in the CRT basis.
+ * plan_e needs no CRT tables: ab_tunnel_create builds its own CRT plan of e' over the moduli of plan_s (root omega_s'^(s'/e')) and
+ * runs every gadget-digit transform in O_e' -- CRT_s'(embed x) is CRT_e'(x) replicated through Lol's embedCRT index. */
 typedef struct ab_tunnel ab_tunnel;
 int ab_tunnel_create(ab_tunnel **out, const ab_plan *plan_r, const ab_plan *plan_e, const ab_plan *plan_s);
 void ab_tunnel_destroy(ab_tunnel *t);
