@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("ALCHEMY_B200_LIB") or os.path.join(_HERE, "lib", "lib
 
 AB_OK, AB_ERR_ARG, AB_ERR_NO_ROOT, AB_ERR_CUDA, AB_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 PLANAR, INTERLEAVED = 0, 1
+RESCALE_POW, RESCALE_LOL_LINEAR = 0, 1      # dec_mask of modSwitch: all polynomials through Pow / c0 through Dec (Lol rescaleLinearMSD)
 OPS = {"crt": 0, "crt_inv": 1, "l": 2, "l_inv": 3, "mul_g_pow": 4, "mul_g_dec": 5, "div_g_pow": 6,
        "div_g_dec": 7, "mul_g_crt": 8, "div_g_crt": 9}
 
@@ -78,11 +79,11 @@ SIGNATURES = {
     "ab_rescale_drop_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "ab_ct_mul_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "ab_mod_switch_work_bytes": (_i64, [_vp, _i64, _i32, _i32, _i32]),
-    "ab_mod_switch_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "ab_mod_switch_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, C.c_uint32, _vp, _vp]),
     "ab_key_switch_work_bytes": (_i64, [_vp, _i64, _i32, _i32]),
     "ab_key_switch_quad_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "ab_mul_key_switch_work_bytes": (_i64, [_vp, _i64, _i32, _i32, _i32, _i32]),
-    "ab_mul_key_switch_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ab_mul_key_switch_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, C.POINTER(_i64), C.c_uint32, _vp, _vp]),
     "ab_tunnel_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, _vp]),
     "ab_tunnel_destroy": (None, [_vp]),
     "ab_tunnel_work_bytes": (_i64, [_vp, _i64, _i32, _i32]),

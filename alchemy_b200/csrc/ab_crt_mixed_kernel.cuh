@@ -97,10 +97,11 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
     }
     (void)skip_program;
     __syncthreads();
-    if (!INV && args.fx.pre_l) mx_l_pass(sm, n, args.fx, q, false);
+    const bool l_on = args.fx.l_period <= 1 || ((args.fx.l_mask >> ((blockIdx.x + args.fx.l_phase) % args.fx.l_period)) & 1) != 0;
+    if (!INV && args.fx.pre_l && l_on) mx_l_pass(sm, n, args.fx, q, false);
     if (wide) run_program<INV, true>(args, sm, tab, q, qinv_neg);
     else run_program<INV, false>(args, sm, tab, q, qinv_neg);
-    if (INV && args.fx.post_linv) mx_l_pass(sm, n, args.fx, q, true);
+    if (INV && args.fx.post_linv && l_on) mx_l_pass(sm, n, args.fx, q, true);
     if (args.fx.store_mode == AB_MX_STORE_SUBSCALE) {
         // RNS rescale epilogue: out = (in - x) * q_drop^-1 mod q   (x = CRT of the lifted dropped limb)
         const int64_t *in = args.fx.sub_in + blockIdx.x * args.fx.sub_ustride + (int64_t)limb * n;

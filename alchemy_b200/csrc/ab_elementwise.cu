@@ -428,6 +428,7 @@ void ab_launch_sub_scale(const ab_plan *p, int64_t *out, int64_t out_bstride, co
 struct CmArgs {
     struct { uint32_t q, up, up_s, pad; uint64_t mu; const uint2 *g; } limb[AB_MAX_LIMBS];
     int32_t nlimbs, nout;      // nout > nlimbs: the product is written at nout limbs, scaled by the appended moduli (rescale up fused)
+    int32_t scaled, pad2;      // every output is multiplied by limb[l].up (appended moduli and / or the caller's per-limb scalar)
     int64_t n, batch;
 };
 __global__ void __launch_bounds__(256) k_ct_mul(const CmArgs a, int64_t *__restrict__ out, const int64_t *__restrict__ x, const int64_t *__restrict__ y) {
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(256) k_ct_mul(const CmArgs a, int64_t *__restr
         const uint32_t c0 = ab_mulmod(a0, b0, q, mu), c2 = ab_mulmod(a1, b1, q, mu);
         const uint32_t c1 = ab_addmod(ab_mulmod(a0, b1, q, mu), ab_mulmod(a1, b0, q, mu), q);
         uint32_t o0 = ab_shoup(c0, g, q), o1 = ab_shoup(c1, g, q), o2 = ab_shoup(c2, g, q);
-        if (a.nout > a.nlimbs) {
+        if (a.scaled) {
             o0 = ab_shoup(o0, a.limb[l].up, a.limb[l].up_s, q);
             o1 = ab_shoup(o1, a.limb[l].up, a.limb[l].up_s, q);
             o2 = ab_shoup(o2, a.limb[l].up, a.limb[l].up_s, q);
@@ -464,15 +465,17 @@ void ab_launch_ct_mul(const ab_plan *p, int64_t *out3, const int64_t *a2, const 
     ab_launch_ct_mul_up(p, out3, a2, b2, batch, nlimbs, nlimbs, st);
 }
 // (*) written directly at nout >= nlimbs limbs: modSwitch up (multiply by the appended moduli, zero limbs) in the same pass
-void ab_launch_ct_mul_up(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, int32_t nout, cudaStream_t st) {
+void ab_launch_ct_mul_up(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, int32_t nout, cudaStream_t st,
+                         const int64_t *prescale) {
     if (batch == 0) return;
     CmArgs a{};
-    a.nlimbs = nlimbs; a.nout = nout; a.n = p->n; a.batch = batch;
+    a.nlimbs = nlimbs; a.nout = nout; a.n = p->n; a.batch = batch; a.scaled = (nout > nlimbs || prescale) ? 1 : 0;
     for (int l = 0; l < nlimbs; ++l) {
         a.limb[l].q = p->limb[l].q; a.limb[l].mu = p->limb[l].mu; a.limb[l].g = reinterpret_cast<const uint2 *>(p->limb[l].g_crt);
         const uint64_t q = (uint64_t)p->q[l];
         uint64_t up = 1;
         for (int k = nlimbs; k < nout; ++k) up = abh::mulmod(up, (uint64_t)p->q[k] % q, q);
+        if (prescale) up = abh::mulmod(up, (uint64_t)(((prescale[l] % (int64_t)q) + (int64_t)q) % (int64_t)q), q);
         a.limb[l].up = (uint32_t)up; a.limb[l].up_s = abh::shoup(up, q);
     }
     k_ct_mul<<<grid_for(batch * nlimbs * p->n, 256, p->sm_count), 256, 0, st>>>(a, out3, a2, b2);

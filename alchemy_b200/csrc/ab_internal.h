@@ -186,6 +186,9 @@ struct AbMxFused {
     // program, post_linv applies L^-1 after an inverse program (Lol `l` / `lInv`: running sums / differences along the
     // p-1 axis of every odd prime); the axes are filled in by the launcher
     int32_t pre_l, post_linv, n_odd, pad2;
+    // l_period > 1: the L passes run only for units u with bit ((u + l_phase) % l_period) of l_mask set (modSwitch of a
+    // ciphertext whose polynomials are rescaled in different bases: Lol rescaleLinearMSD takes c0 in Dec, c1 in Pow [RECALL])
+    int32_t l_period, l_mask, l_phase, pad3;
     int64_t dst_ustride;             // 0: units are contiguous in the destination; else int64 words between consecutive units
     struct { int32_t d, rts; } odd[AB_MAX_AXES];
     // AB_MX_STORE_SUBSCALE: y = (sub_in - x) * scale[limb]
@@ -291,7 +294,7 @@ void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, 
 // whole PT2CT mul_ pipeline in one kernel for small power-of-two rings with TrivGad (ab_mulks_pow2.cu)
 bool ab_mulks_pow2_supported(const ab_plan *p, int32_t lin, int32_t lh, int32_t lout, int32_t base);
 void ab_launch_mulks_pow2(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
-                          int32_t lin, int32_t lh, int32_t lout, cudaStream_t st);
+                          int32_t lin, int32_t lh, int32_t lout, cudaStream_t st, const int64_t *prescale = nullptr);
 bool ab_mixed_mac_supported(const ab_plan *p, int32_t nlimbs);
 int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs);
 int32_t ab_mixed_mac_parts(const ab_plan *p, int64_t units, int32_t nlimbs, int32_t total_digits);   // how many CTAs per unit pay off

@@ -14,7 +14,9 @@ void ab_launch_lift_reduce(const ab_plan *p, int64_t *out, int64_t out_bstride, 
 void ab_launch_sub_scale(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *in, int64_t in_bstride,
                          const int64_t *corr, int64_t corr_bstride, int64_t batch, int32_t nl, const int64_t *scal, cudaStream_t st);
 void ab_launch_ct_mul(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, cudaStream_t st);
-void ab_launch_ct_mul_up(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, int32_t nout, cudaStream_t st);
+// prescale (HOST, nlimbs residues, may be null): every coefficient of the product is also multiplied by prescale[l] (toMSD: p^-1 mod q_l)
+void ab_launch_ct_mul_up(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, int32_t nout, cudaStream_t st,
+                         const int64_t *prescale = nullptr);
 void ab_launch_hint_ip(const ab_plan *p, int64_t *out, int64_t out_bstride, const int64_t *dig, int64_t dig_bstride, const int64_t *hint,
                        const int64_t *add, int64_t add_bstride, bool accumulate, int64_t batch, int32_t nlimbs, int32_t ndig, cudaStream_t st);
 // hints pre-multiplied by 2^32 / 2^48 (uint2 per residue), then the inner product with one reduction per output

@@ -7,7 +7,8 @@
 // 32 n L_in + 16 n L_out bytes per op, hints amortised over the batch (they stay in L2).
 //
 // Steps (same order and arithmetic as the separate kernels of ab_she.cpp, so results are bit-identical):
-//   A  (c0,c1,c2) = (a0 b0, a0 b1 + a1 b0, a1 b1)              (g = 1: a power of two has no odd prime)
+//   A  (c0,c1,c2) = (a0 b0, a0 b1 + a1 b0, a1 b1)              (g = 1: a power of two has no odd prime), times the caller's
+//      per-limb scalar (Lol toMSD: p^-1 mod q_l) when one is given
 //   B  modSwitch up L_in -> L_h: multiply by the new moduli, new limbs are zero
 //   C  TrivGad key switch: c2 -> powerful basis per limb (crtInv); digit d = centred limb d, reduced into every
 //      other modulus and transformed (digit d in limb d is c2's CRT form itself); (c0,c1) += sum_d digit_d * hint_d
@@ -29,6 +30,7 @@ struct MkArgs {
     } limb[AB_MAX_LIMBS];
     uint32_t dinv[AB_MAX_LIMBS][AB_MAX_LIMBS], dinv_s[AB_MAX_LIMBS][AB_MAX_LIMBS];   // [d][l] = q_d^-1 mod q_l
     int32_t logn, lin, lh, lout;
+    int32_t scaled, pad;       // the product is multiplied by limb[l].up: appended moduli (L_h > L_in) and / or the caller's per-limb scalar (toMSD)
     int64_t batch;
 };
 
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(256) k_mulks_pow2(const __grid_constant__ MkAr
         uint32_t c0 = ab_mulmod(a0, b0, q, mu);
         uint32_t c1 = ab_addmod(ab_mulmod(a0, b1, q, mu), ab_mulmod(a1, b0, q, mu), q);
         uint32_t c2 = ab_mulmod(a1, b1, q, mu);
-        if (lh > lin) {
+        if (a.scaled) {
             c0 = ab_shoup(c0, a.limb[l].up, a.limb[l].up_s, q);
             c1 = ab_shoup(c1, a.limb[l].up, a.limb[l].up_s, q);
             c2 = ab_shoup(c2, a.limb[l].up, a.limb[l].up_s, q);
@@ -210,11 +212,11 @@ bool ab_mulks_pow2_supported(const ab_plan *p, int32_t lin, int32_t lh, int32_t 
 }
 
 void ab_launch_mulks_pow2(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
-                          int32_t lin, int32_t lh, int32_t lout, cudaStream_t st) {
+                          int32_t lin, int32_t lh, int32_t lout, cudaStream_t st, const int64_t *prescale) {
     AB_REQUIRE(ab_mulks_pow2_supported(p, lin, lh, lout, 0), AB_ERR_UNSUPPORTED, "fused mul + key switch: not supported for this plan");
     if (batch == 0) return;
     MkArgs a{};
-    a.logn = p->logn; a.lin = lin; a.lh = lh; a.lout = lout; a.batch = batch;
+    a.logn = p->logn; a.lin = lin; a.lh = lh; a.lout = lout; a.batch = batch; a.scaled = (lh > lin || prescale) ? 1 : 0;
     for (int l = 0; l < lh; ++l) {
         const AbLimbDev &ld = p->limb[l];
         const uint64_t q = (uint64_t)p->q[l];
@@ -223,6 +225,7 @@ void ab_launch_mulks_pow2(const ab_plan *p, int64_t *out2, const int64_t *a2, co
         a.limb[l].inv = reinterpret_cast<const uint2 *>(ld.tw_inv_flat);
         uint64_t up = 1;
         for (int k = lin; k < lh; ++k) up = abh::mulmod(up, (uint64_t)p->q[k] % q, q);
+        if (prescale && l < lin) up = abh::mulmod(up, (uint64_t)(((prescale[l] % (int64_t)q) + (int64_t)q) % (int64_t)q), q);
         a.limb[l].up = (uint32_t)up; a.limb[l].up_s = abh::shoup(up, q);
         for (int d = 0; d < lh; ++d)
             if (d != l) {

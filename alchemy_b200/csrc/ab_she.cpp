@@ -47,6 +47,8 @@ static void fill_digits(const ab_plan *p, int32_t nlimbs, int32_t base, AbMxFuse
     fx.gbase = base;
 }
 static bool fused_ok(const ab_plan *p, int32_t nlimbs, const void *a, const void *b) {
+    static const bool off = getenv("AB_NO_FUSE") && atoi(getenv("AB_NO_FUSE")) != 0;      // A/B measurements only: plain launch sequences
+    if (off) return false;
     return !ab_pow2_supported(p) && ab_mixed_supported(p, AbView{(int64_t *)a, 1, 0, nlimbs, AB_LAYOUT_PLANAR}) && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
 }
 
@@ -76,24 +78,45 @@ extern "C" int64_t ab_mod_switch_work_bytes(const ab_plan *p, int64_t batch, int
     const int64_t rw = ms_row_words(p, from, to);
     return chunk_of(batch * npoly, rw * 8) * rw * 8;
 }
-static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, int64_t rows, int32_t from, int32_t to, int64_t *work, cudaStream_t st) {
+// Which basis each polynomial of a ciphertext is rescaled in: bit i of dec_mask set = polynomial i goes through the DECODING basis
+// (L^-1 after the inverse transform of the dropped limbs, L before the forward transform of the correction), clear = powerful basis.
+// Rows are polynomials: row r of the call is polynomial (r + phase) % period of its ciphertext.  Rings without odd primes have L = id.
+struct MsBasis {
+    int32_t period = 1;
+    uint32_t mask = 0;
+    bool any(const ab_plan *p) const {
+        if ((mask & ((period >= 32 ? 0u : (1u << period)) - 1u)) == 0) return false;
+        for (const AbAxis &ax : p->axes) if (ax.p != 2) return true;
+        return false;
+    }
+    void apply(AbMxFused &f, bool inverse, int64_t row0) const {
+        if (inverse) f.post_linv = 1; else f.pre_l = 1;
+        f.l_period = period; f.l_mask = (int32_t)mask; f.l_phase = (int32_t)(row0 % period);
+    }
+};
+
+// `rows` polynomials; row r is read at in + r*in_stride (from limbs) and written at out + r*out_stride (to limbs)
+static void mod_switch_rows(const ab_plan *p, int64_t *out, int64_t out_stride, const int64_t *in, int64_t in_stride, int64_t rows, int32_t from, int32_t to,
+                            int64_t *work, cudaStream_t st, const MsBasis &basis, bool can_fuse) {
     const int64_t n = p->n;
     if (to >= from) {
-        if (to == from) ab_launch_copy_rows(out, from * n, in, from * n, from * n, rows, st);
-        else ab_launch_rescale_up(p, out, to * n, in, from * n, rows, from, to, st);
+        if (to == from) ab_launch_copy_rows(out, out_stride, in, in_stride, from * n, rows, st);
+        else ab_launch_rescale_up(p, out, out_stride, in, in_stride, rows, from, to, st);
         return;
     }
+    const bool dec = basis.any(p);
+    AB_REQUIRE(!dec || can_fuse || basis.period == 1, AB_ERR_UNSUPPORTED, "mixed rescale bases need the per-polynomial route");
     const int64_t rw = ms_row_words(p, from, to);
     const int64_t chunk = chunk_of(rows, rw * 8);
     for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
         const int64_t R = std::min(chunk, rows - r0);
         int64_t *dropped = work, *lifted = dropped + R * n, *ping = lifted + R * (from - 1) * n, *pong = ping + R * (from - 1) * n;
-        const int64_t *cur = in + r0 * from * n;
-        int64_t cur_stride = from * n;
+        const int64_t *cur = in + r0 * in_stride;
+        int64_t cur_stride = in_stride;
         for (int32_t L = from; L > to; --L) {
             const int32_t d = L - 1;
             static const bool no_multi = getenv("AB_NO_MULTIDROP") && atoi(getenv("AB_NO_MULTIDROP")) != 0;      // A/B measurements only
-            if (!no_multi && L - to >= 2 && fused_ok(p, L, cur, work) && ((uintptr_t)out & 15) == 0 && ((cur_stride * 8) % 16) == 0) {
+            if (can_fuse && !no_multi && L - to >= 2) {
                 // drop k = min(L - to, 4) limbs in ONE rescale: crtInv of the k dropped limbs in one launch, then one kernel per
                 // batch that rebuilds, per coefficient, the centred digits of the sequential drops (Garner), reduces
                 // x = r_0 + q_0 (r_1 + ...) into each kept modulus, transforms it and applies (in - x) (q_0 q_1 ...)^-1:
@@ -101,9 +124,11 @@ static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, i
                 const int32_t k = std::min<int32_t>(L - to, AB_MX_MAX_DROP), keep = L - k;
                 AbMxFused fi{};
                 fi.load_mode = AB_MX_LOAD_SRC; fi.src = cur; fi.src_ustride = cur_stride; fi.src_limb0 = keep;
+                if (dec) basis.apply(fi, true, r0);
                 ab_launch_crt_mixed_fused(p, AbView{dropped, R, keep, k, AB_LAYOUT_PLANAR}, true, &fi, st);    // [R][k][n], ascending limbs
                 AbMxFused fx{};
                 fx.load_mode = AB_MX_LOAD_GARNER; fx.store_mode = AB_MX_STORE_SUBSCALE;
+                if (dec) basis.apply(fx, false, r0);
                 // drop order: i = 0 is limb L-1; the kernel reads src + i*n, so point it at the last limb and step backwards
                 fx.src = dropped + (int64_t)(k - 1) * n; fx.src_ustride = (int64_t)k * n; fx.gar_k = k;
                 for (int i = 0; i < k; ++i) {
@@ -123,21 +148,25 @@ static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, i
                     const uint64_t inv = abh::invmod(prod, qk);
                     fx.scale[kk] = (uint32_t)inv; fx.scale_s[kk] = abh::shoup(inv, qk);
                 }
-                int64_t *dst_buf = (keep == to) ? out + r0 * to * n : ((cur == ping) ? pong : ping);
+                int64_t *dst_buf;
+                if (keep == to) { dst_buf = out + r0 * out_stride; fx.dst_ustride = out_stride; }
+                else dst_buf = (cur == ping) ? pong : ping;
                 ab_launch_crt_mixed_fused(p, AbView{dst_buf, R, 0, keep, AB_LAYOUT_PLANAR}, false, &fx, st);
                 cur = dst_buf;
-                cur_stride = (int64_t)keep * n;
+                cur_stride = keep == to ? out_stride : (int64_t)keep * n;
                 L = keep + 1;          // the loop's --L lands on `keep`
                 continue;
             }
-            if (fused_ok(p, L, cur, work) && ((uintptr_t)out & 15) == 0 && ((cur_stride * 8) % 16) == 0) {
+            if (can_fuse) {
                 // two launches per dropped limb: crtInv of that limb (out of place), then one kernel that lifts it,
                 // reduces it into each kept modulus, transforms it and applies (in - x) * q_d^-1 on the way out
                 AbMxFused fi{};
                 fi.load_mode = AB_MX_LOAD_SRC; fi.src = cur; fi.src_ustride = cur_stride; fi.src_limb0 = d;   // view limb0 = d selects the modulus
+                if (dec) basis.apply(fi, true, r0);
                 ab_launch_crt_mixed_fused(p, AbView{dropped, R, d, 1, AB_LAYOUT_PLANAR}, true, &fi, st);
                 AbMxFused fx{};
                 fx.load_mode = AB_MX_LOAD_DIGITS; fx.store_mode = AB_MX_STORE_SUBSCALE;
+                if (dec) basis.apply(fx, false, r0);
                 fx.nd = 1; fx.gbase = 0; fx.src = dropped; fx.src_ustride = n; fx.n_src = (int32_t)n; fx.gK = 1;
                 fx.dig[0].q_src = (uint32_t)p->q[d]; fx.dig[0].limb = 0; fx.dig[0].pw = 1; fx.dig[0].H = 0; fx.dig[0].last = 1;
                 fx.sub_in = cur; fx.sub_ustride = cur_stride;
@@ -145,23 +174,28 @@ static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, i
                     const uint64_t inv = abh::invmod((uint64_t)p->q[d] % (uint64_t)p->q[k], (uint64_t)p->q[k]);
                     fx.scale[k] = (uint32_t)inv; fx.scale_s[k] = abh::shoup(inv, (uint64_t)p->q[k]);
                 }
-                int64_t *dst_buf = (d == to) ? out + r0 * to * n : ((cur == ping) ? pong : ping);
+                int64_t *dst_buf;
+                if (d == to) { dst_buf = out + r0 * out_stride; fx.dst_ustride = out_stride; }
+                else dst_buf = (cur == ping) ? pong : ping;
                 ab_launch_crt_mixed_fused(p, AbView{dst_buf, R, 0, d, AB_LAYOUT_PLANAR}, false, &fx, st);
                 cur = dst_buf;
-                cur_stride = (int64_t)d * n;
+                cur_stride = d == to ? out_stride : (int64_t)d * n;
                 continue;
             }
+            // launch sequence (power-of-two rings, rings outside the shared-memory kernel): here every row shares one basis
             ab_launch_copy_rows(dropped, n, cur + (int64_t)d * n, cur_stride, n, R, st);
             ab_crt_rows(p, dropped, R, d, true, st);
+            if (dec) ab_launch_prime_op(p, AB_PR_LINV, AbView{dropped, R, d, 1, AB_LAYOUT_PLANAR}, st);
             int32_t dst[AB_MAX_LIMBS];
             for (int k = 0; k < d; ++k) dst[k] = k;
             ab_launch_lift_reduce(p, lifted, (int64_t)d * n, dropped, n, R, d, dst, d, st);
+            if (dec) ab_launch_prime_op(p, AB_PR_L, AbView{lifted, R, 0, d, AB_LAYOUT_PLANAR}, st);
             ab_crt_dispatch(p, AbView{lifted, R, 0, d, AB_LAYOUT_PLANAR}, false, st);
             int64_t scal[AB_MAX_LIMBS];
             for (int k = 0; k < d; ++k) scal[k] = (int64_t)abh::invmod((uint64_t)p->q[d] % (uint64_t)p->q[k], (uint64_t)p->q[k]);
             int64_t *dst_buf;
             int64_t dst_stride;
-            if (d == to) { dst_buf = out + r0 * to * n; dst_stride = (int64_t)to * n; }
+            if (d == to) { dst_buf = out + r0 * out_stride; dst_stride = out_stride; }
             else { dst_buf = (cur == ping) ? pong : ping; dst_stride = (int64_t)d * n; }
             ab_launch_sub_scale(p, dst_buf, dst_stride, cur, cur_stride, lifted, (int64_t)d * n, R, d, scal, st);
             cur = dst_buf;
@@ -169,14 +203,31 @@ static void mod_switch_rows(const ab_plan *p, int64_t *out, const int64_t *in, i
         }
     }
 }
+static void mod_switch_polys(const ab_plan *p, int64_t *out, const int64_t *in, int64_t batch, int32_t npoly, int32_t from, int32_t to, uint32_t dec_mask,
+                             int64_t *work, cudaStream_t st) {
+    const int64_t n = p->n;
+    MsBasis basis;
+    basis.period = npoly; basis.mask = dec_mask;
+    const bool can_fuse = to < from && fused_ok(p, from, in, work) && ((uintptr_t)out & 15) == 0;
+    if (to >= from || !basis.any(p) || can_fuse) {
+        mod_switch_rows(p, out, (int64_t)to * n, in, (int64_t)from * n, batch * npoly, from, to, work, st, basis, can_fuse);
+        return;
+    }
+    // launch-sequence route with polynomials in different bases: one pass per polynomial index, rows strided by the ciphertext
+    for (int32_t i = 0; i < npoly; ++i) {
+        MsBasis one;
+        one.period = 1; one.mask = (dec_mask >> i) & 1u;
+        mod_switch_rows(p, out + (int64_t)i * to * n, (int64_t)npoly * to * n, in + (int64_t)i * from * n, (int64_t)npoly * from * n, batch, from, to, work, st, one, false);
+    }
+}
 extern "C" int ab_mod_switch_dev(const ab_plan *p, int64_t *out, const int64_t *in, int64_t batch, int32_t npoly, int32_t from, int32_t to,
-                                 void *work, void *stream) {
+                                 uint32_t dec_mask, void *work, void *stream) {
     return ab_guard([&] {
         AB_REQUIRE(p && ((out && in) || batch == 0), AB_ERR_ARG, "null argument");
         AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan has no CRT tables");
-        AB_REQUIRE(batch >= 0 && npoly >= 1 && from >= 1 && to >= 1 && from <= p->L && to <= p->L, AB_ERR_ARG, "bad limb counts");
+        AB_REQUIRE(batch >= 0 && npoly >= 1 && npoly <= 31 && from >= 1 && to >= 1 && from <= p->L && to <= p->L, AB_ERR_ARG, "bad limb counts");
         AB_REQUIRE(to >= from || work != nullptr, AB_ERR_ARG, "null scratch buffer");
-        mod_switch_rows(p, out, in, batch * npoly, from, to, (int64_t *)work, (cudaStream_t)stream);
+        mod_switch_polys(p, out, in, batch, npoly, from, to, dec_mask, (int64_t *)work, (cudaStream_t)stream);
     });
 }
 
@@ -489,6 +540,9 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
 
 // ------------------------------------------------------------------------------------ PT2CT mul_ as one entry
 // modSwitch (to l_out) . keySwitchQuad hint . modSwitch (to l_hint) . (*)   -- Crypto/Alchemy/Interpreter/PT2CT.hs:172-177.
+// Lol's (*) returns an LSD ciphertext and modSwitch / keySwitchQuadCirc first bring it to MSD form (toMSD: every polynomial times
+// p^-1 mod q_l; ModSwitchCtx_ carries ToSDCtx, Eval.hs:124): the caller passes those per-limb scalars as `prescale` (null = the
+// inputs are taken as they are, e.g. already pre-scaled) and keeps the (k, l) bookkeeping on its side.
 // Small power-of-two rings with TrivGad run as ONE kernel with every intermediate in shared memory
 // (ab_mulks_pow2.cu); everything else as the sequence of the entries above, intermediates in `work`.
 static int64_t mks_inter_words(const ab_plan *p, int64_t batch, int32_t lin, int32_t lh) {
@@ -503,14 +557,14 @@ extern "C" int64_t ab_mul_key_switch_work_bytes(const ab_plan *p, int64_t batch,
     return mks_inter_words(p, batch, lin, lh) * 8 + std::max(w1, std::max(w2, w3)) + 64;
 }
 extern "C" int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
-                                     int32_t lin, int32_t lh, int32_t lout, int32_t base, void *work, void *stream) {
+                                     int32_t lin, int32_t lh, int32_t lout, int32_t base, const int64_t *prescale, uint32_t dec_mask, void *work, void *stream) {
     return ab_guard([&] {
         AB_REQUIRE(p && ((out2 && a2 && b2 && hint) || batch == 0), AB_ERR_ARG, "null argument");
         AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan has no CRT tables");
         AB_REQUIRE(batch >= 0 && lin >= 1 && lh >= 1 && lout >= 1 && lin <= p->L && lh <= p->L && lout <= p->L, AB_ERR_ARG, "bad batch or limb counts");
         if (batch == 0) return;
         if (ab_mulks_pow2_supported(p, lin, lh, lout, base)) {
-            ab_launch_mulks_pow2(p, out2, a2, b2, hint, batch, lin, lh, lout, (cudaStream_t)stream);
+            ab_launch_mulks_pow2(p, out2, a2, b2, hint, batch, lin, lh, lout, (cudaStream_t)stream, prescale);      // no odd prime: Dec = Pow
             return;
         }
         AB_REQUIRE(work != nullptr, AB_ERR_ARG, "null scratch buffer");
@@ -518,13 +572,14 @@ extern "C" int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int6
         int64_t *c3 = (int64_t *)work, *c3h = c3 + batch * 3 * lin * n, *c2h = c3h + batch * 3 * lh * n;
         void *w = c2h + batch * 2 * lh * n;
         auto must = [](int rc) { if (rc != AB_OK) throw ab_error{rc, ab_last_error()}; };
+        // (*) yields an LSD ciphertext; modSwitch starts with toMSD = every polynomial times p^-1 mod q_l (`prescale`), folded into the product
         if (lh >= lin) {
-            ab_launch_ct_mul_up(p, c3h, a2, b2, batch, lin, lh, (cudaStream_t)stream);      // product and scale-up in one pass
+            ab_launch_ct_mul_up(p, c3h, a2, b2, batch, lin, lh, (cudaStream_t)stream, prescale);      // product, toMSD and scale-up in one pass
         } else {
-            must(ab_ct_mul_dev(p, c3, a2, b2, batch, lin, stream));
-            must(ab_mod_switch_dev(p, c3h, c3, batch, 3, lin, lh, w, stream));
+            ab_launch_ct_mul_up(p, c3, a2, b2, batch, lin, lin, (cudaStream_t)stream, prescale);
+            must(ab_mod_switch_dev(p, c3h, c3, batch, 3, lin, lh, dec_mask, w, stream));
         }
         must(ab_key_switch_quad_dev(p, c2h, c3h, hint, batch, lh, base, w, stream));
-        must(ab_mod_switch_dev(p, out2, c2h, batch, 2, lh, lout, w, stream));
+        must(ab_mod_switch_dev(p, out2, c2h, batch, 2, lh, lout, dec_mask, w, stream));
     });
 }

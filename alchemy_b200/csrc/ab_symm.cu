@@ -134,14 +134,14 @@ struct RlArgs {
     double pw_d[AB_MAX_LIMBS];                     // q_0 ... q_(i-1) / Q
     uint64_t Q_p;                                  // Q mod pmod
     uint64_t pmod;
-    int32_t nlimbs, pad;
+    int32_t nlimbs, gx;                            // gx: CTAs per ring element (the batch index lives in blockIdx.x / gx: no 65535 cap)
     int64_t n, batch;
 };
 __global__ void __launch_bounds__(256) k_rns_lift_reduce(const RlArgs a, int64_t *__restrict__ out, double *__restrict__ rate, const int64_t *__restrict__ in) {
     __shared__ double smax[256];
-    const int64_t b = blockIdx.y;
+    const int64_t b = blockIdx.x / a.gx;
     double mx = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t j = (int64_t)(blockIdx.x % a.gx) * blockDim.x + threadIdx.x; j < a.n; j += (int64_t)a.gx * blockDim.x) {
         uint32_t v[AB_MAX_LIMBS];
         const int64_t *ip = in + b * a.nlimbs * a.n + j;
 #pragma unroll
@@ -158,10 +158,21 @@ __global__ void __launch_bounds__(256) k_rns_lift_reduce(const RlArgs a, int64_t
             if (v[i] != a.half[i]) { neg = v[i] > a.half[i]; break; }
         // value mod pmod, and |value| / Q as a double (diagnostic: errorRate)
         unsigned __int128 acc = 0;
-        double xd = 0.0;
-        for (int i = 0; i < a.nlimbs; ++i) { acc += (unsigned __int128)v[i] * a.pw_p[i]; xd += (double)v[i] * a.pw_d[i]; }
+        for (int i = 0; i < a.nlimbs; ++i) acc += (unsigned __int128)v[i] * a.pw_p[i];
         uint64_t r = (uint64_t)(acc % a.pmod);
-        if (neg) { r = (r + a.pmod - a.Q_p) % a.pmod; xd = 1.0 - xd; }
+        if (neg) {
+            r = (r + a.pmod - a.Q_p) % a.pmod;
+            // |x| = Q - x = 1 + sum (q_i - 1 - v_i) P_i: take ITS mixed-radix digits (complement plus a carry) so that a small
+            // magnitude keeps its leading digits zero -- 1.0 - x/Q would cancel to an absolute error of 1e-16 (error rates are far smaller)
+            uint32_t carry = 1;
+            for (int i = 0; i < a.nlimbs; ++i) {
+                uint32_t w = a.q[i] - 1u - v[i] + carry;
+                carry = w == a.q[i];
+                v[i] = carry ? 0u : w;
+            }
+        }
+        double xd = 0.0;                        // most significant digit last: the small terms are summed first
+        for (int i = 0; i < a.nlimbs; ++i) xd += (double)v[i] * a.pw_d[i];
         out[b * a.n + j] = (int64_t)r;
         mx = fmax(mx, xd);
     }
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(256) k_rns_lift_reduce(const RlArgs a, int64_t
 extern "C" int ab_rns_lift_reduce_dev(const ab_plan *p, int64_t *out, double *maxrate, const int64_t *in, int64_t batch, int32_t nlimbs, int64_t pmod, void *stream) {
     return ab_guard([&] {
         AB_REQUIRE(p && ((out && in) || batch == 0), AB_ERR_ARG, "null argument");
-        AB_REQUIRE(batch >= 0 && batch < 65536 && nlimbs >= 1 && nlimbs <= p->L && pmod >= 2 && pmod < (1ll << 62), AB_ERR_ARG, "bad batch, limb count or plaintext modulus");
+        AB_REQUIRE(batch >= 0 && nlimbs >= 1 && nlimbs <= p->L && pmod >= 2 && pmod < (1ll << 62), AB_ERR_ARG, "bad batch, limb count or plaintext modulus");
         if (batch == 0) return;
         RlArgs a{};
         a.nlimbs = nlimbs; a.n = p->n; a.batch = batch; a.pmod = (uint64_t)pmod;
@@ -224,7 +235,9 @@ extern "C" int ab_rns_lift_reduce_dev(const ab_plan *p, int64_t *out, double *ma
         cudaStream_t st = (cudaStream_t)stream;
         if (maxrate) AB_CHECK_CUDA(cudaMemsetAsync(maxrate, 0, (size_t)batch * sizeof(double), st));
         const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((p->n + 255) / 256, 64));
-        k_rns_lift_reduce<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(a, out, maxrate, in);
+        AB_REQUIRE(batch * (int64_t)gx < (1ll << 31), AB_ERR_ARG, "batch too large for one launch");
+        a.gx = (int32_t)gx;
+        k_rns_lift_reduce<<<(unsigned)(batch * gx), 256, 0, st>>>(a, out, maxrate, in);
         ab_count_launch();
         ab_check_launch("rns_lift_reduce");
     });

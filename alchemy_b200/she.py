@@ -27,8 +27,9 @@ def ctMul(plan: Plan, a, b):
     return out
 
 
-def modSwitch(plan: Plan, c, to_limbs):
-    """rescaleCyc on every coefficient: [B,P,from,n] -> [B,P,to,n] over the leading moduli of the plan"""
+def modSwitch(plan: Plan, c, to_limbs, dec_mask=0):
+    """rescaleCyc on every coefficient of an MSD ciphertext: [B,P,from,n] -> [B,P,to,n] over the leading moduli of the plan.
+    dec_mask bit i: polynomial i is rounded in the decoding basis (1 = Lol's rescaleLinearMSD: c0 Dec, the rest Pow; 0 = all Pow)"""
     B, P, frm, n = c.shape
     assert n == plan.n
     if to_limbs == frm:
@@ -37,7 +38,7 @@ def modSwitch(plan: Plan, c, to_limbs):
     nbytes = lib().ab_mod_switch_work_bytes(plan.h, B, P, frm, to_limbs)
     assert nbytes >= 0
     work = _work(nbytes, c.device)
-    check(lib().ab_mod_switch_dev(plan.h, _ptr(out), _ptr(c), B, P, frm, to_limbs, C.c_void_p(work.data_ptr()), _stream()))
+    check(lib().ab_mod_switch_dev(plan.h, _ptr(out), _ptr(c), B, P, frm, to_limbs, dec_mask, C.c_void_p(work.data_ptr()), _stream()))
     return out
 
 
@@ -52,14 +53,20 @@ def keySwitchQuadCirc(plan: Plan, c3, hint, base=0):
     return out
 
 
-def mulKeySwitch(plan: Plan, a, b, hint, l_hint, l_out, base=0):
+def mulKeySwitch(plan: Plan, a, b, hint, l_hint, l_out, base=0, prescale=None, dec_mask=0):
     """PT2CT `mul_` (PT2CT.hs:172-177): modSwitch . keySwitchQuad hint . modSwitch . (*)
-    a, b at L_in limbs; the hint lives at l_hint limbs; the result at l_out limbs."""
+    a, b at L_in limbs (LSD forms); the hint lives at l_hint limbs; the result (MSD form) at l_out limbs.
+    prescale: per-limb scalars of Lol's toMSD (p^-1 mod q_l for the L_in moduli) folded into the product; None = 1
+    (symm.SymmSHE.mulKeySwitch passes them and keeps the (k, l) bookkeeping).  dec_mask: as in modSwitch."""
     B, two, lin, n = a.shape
     assert two == 2 and b.shape == a.shape and n == plan.n and hint.shape[2] == l_hint
     out = torch.empty((B, 2, l_out, n), dtype=torch.int64, device=a.device)
     work = _work(lib().ab_mul_key_switch_work_bytes(plan.h, B, lin, l_hint, l_out, base), a.device)
-    check(lib().ab_mul_key_switch_dev(plan.h, _ptr(out), _ptr(a), _ptr(b), _ptr(hint), B, lin, l_hint, l_out, base,
+    ps = None
+    if prescale is not None:
+        assert len(prescale) == lin
+        ps = (C.c_int64 * lin)(*[int(v) for v in prescale])
+    check(lib().ab_mul_key_switch_dev(plan.h, _ptr(out), _ptr(a), _ptr(b), _ptr(hint), B, lin, l_hint, l_out, base, ps, dec_mask,
                                       C.c_void_p(work.data_ptr()), _stream()))
     return out
 

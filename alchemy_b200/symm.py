@@ -33,6 +33,11 @@ class CT:
 
 
 class SymmSHE:
+    # which polynomials modSwitch rounds in the decoding basis (bit i = c_i): Lol's rescaleLinearMSD takes c0 through rescaleDec and
+    # c1 through rescalePow [RECALL; generalised here to "c0 Dec, every further coefficient Pow" for the degree-2 ciphertext that
+    # PT2CT.hs:177 rescales before the key switch].  0 = every polynomial through the powerful basis.
+    rescale_dec_mask = 1
+
     def __init__(self, m, mp, moduli, p):
         assert mp % m == 0
         self.m, self.mp, self.moduli, self.p = m, mp, [int(q) for q in moduli], int(p)
@@ -99,17 +104,21 @@ class SymmSHE:
         return torch.stack([h0, mask], dim=1).contiguous()
 
     # ---- the same with device randomness (KeysHints.hs:96 getKey / genSK, :113 getQuadCircHint) -------------------
-    # stream ids: 0 secret key, 1 encryption noise, 2 encryption mask, 3 hint noise, 4 hint mask
-    def sampleSK(self, cdt, seed):
-        return self.genSK(GT.gaussianDec(self.hi, 1, cdt, seed, 0)[0])
+    # stream ids: 0 secret key, 1 encryption noise, 2 encryption mask, 3 hint noise, 4 hint mask; + 8 * nonce.
+    # TEST AND BENCHMARK RANDOMNESS ONLY: Philox4x32-10 is a statistical generator with a 64-bit key, not a CSPRNG, and every draw
+    # is a pure function of (seed, stream id, position) -- two calls with the same (seed, nonce) produce the SAME masks and noise.
+    # Give every call of one key's lifetime its own nonce (or seed); production keys need a cryptographic generator behind the
+    # same entry points (the kernels take masks and noise as inputs: encrypt / ksQuadCircHint / tunnelHint above and below).
+    def sampleSK(self, cdt, seed, nonce=0):
+        return self.genSK(GT.gaussianDec(self.hi, 1, cdt, seed, 0 + 8 * nonce)[0])
 
-    def sampleKSQuadCircHint(self, sk, L, cdt, seed, base=0):
+    def sampleKSQuadCircHint(self, sk, L, cdt, seed, base=0, nonce=0):
         D = GT.gadgetLen(self.hi, L, base)
-        return self.ksQuadCircHint(sk, GT.uniform(self.hi, D, L, seed, 4), GT.gaussianDec(self.hi, D, cdt, seed, 3), L, base)
+        return self.ksQuadCircHint(sk, GT.uniform(self.hi, D, L, seed, 4 + 8 * nonce), GT.gaussianDec(self.hi, D, cdt, seed, 3 + 8 * nonce), L, base)
 
-    def encryptRandom(self, sk, mu, L, cdt, seed):
+    def encryptRandom(self, sk, mu, L, cdt, seed, nonce=0):
         B = mu.shape[0]
-        return self.encrypt(sk, mu, GT.gaussianDec(self.hi, B, cdt, seed, 1), GT.uniform(self.hi, B, L, seed, 2))
+        return self.encrypt(sk, mu, GT.gaussianDec(self.hi, B, cdt, seed, 1 + 8 * nonce), GT.uniform(self.hi, B, L, seed, 2 + 8 * nonce))
 
     # ---- encrypt / decrypt ---------------------------------------------------------------------
     def encrypt(self, sk, mu, noise_dec, c1):
@@ -215,7 +224,18 @@ class SymmSHE:
 
     def modSwitch(self, ct, to_limbs):
         ct = self.toMSD(ct)
-        return CT(she.modSwitch(self.hi, ct.c, to_limbs), ct.k, ct.l, "MSD")
+        return CT(she.modSwitch(self.hi, ct.c, to_limbs, self.rescale_dec_mask), ct.k, ct.l, "MSD")
+
+    def mulKeySwitch(self, a, b, hint, l_hint, l_out, base=0):
+        """PT2CT `mul_` (PT2CT.hs:172-177) = modSwitch . keySwitchQuad hint . modSwitch . (*) as ONE ABI call.  (*) works on LSD
+        forms and yields an LSD ciphertext; the first modSwitch begins with toMSD (polynomials times p^-1 mod q_l, l times -Q_in
+        mod p): the scalars ride along in the product kernel.  Bit-identical to self.modSwitch(self.keySwitchQuad(self.modSwitch(
+        self.mul(a, b), l_hint), hint, base), l_out)."""
+        a, b = self.toLSD(a), self.toLSD(b)
+        assert a.L == b.L
+        pre = [pow(self.p, -1, q) for q in self.moduli[:a.L]]
+        c = she.mulKeySwitch(self.hi, a.c, b.c, hint, l_hint, l_out, base, prescale=pre, dec_mask=self.rescale_dec_mask)
+        return CT(c, a.k + b.k + 1, a.l * b.l * (-self._Q(a.L)) % self.p, "MSD")
 
     def keySwitchQuad(self, ct, hint, base=0):
         ct = self.toMSD(ct)

@@ -171,23 +171,25 @@ def mul_keyswitch_leg(ab, torch, iters=5):
     HomomRLWR's deepest level (m' = 20475, n = 8640, L 4 -> hint 5 -> 3, TrivGad) and Arithmetic.hs (m' = 512, 2 -> 2 -> 1)."""
     from alchemy_b200 import she
     out = []
-    for name, m, moduli, lin, lh, lout, B in (
-            ("HomomRLWR level 1", 20475, [1543651201, 689270401, 718099201, 720720001, 1556755201, 1567238401], 4, 5, 3, 1024),
-            ("Arithmetic", 512, [268440577, 8392193, 1073750017], 2, 2, 1, 16384)):
+    for name, m, moduli, lin, lh, lout, B, pt in (
+            ("HomomRLWR level 1", 20475, [1543651201, 689270401, 718099201, 720720001, 1556755201, 1567238401], 4, 5, 3, 1024, 32),
+            ("Arithmetic", 512, [268440577, 8392193, 1073750017], 2, 2, 1, 16384, 7)):
         plan = ab.Plan(m, moduli)
         n = plan.n
         rnd = lambda lead, L: torch.stack([torch.randint(0, q, tuple(lead) + (n,), dtype=torch.int64, device="cuda") for q in moduli[:L]], dim=-2)
         a, b = rnd((B, 2), lin), rnd((B, 2), lin)
         hint = rnd((lh, 2), lh)
+        # Lol's sequence: (*) on LSD forms, toMSD scalars p^-1 mod q_l folded into the product, c0 rounded in the decoding basis
+        kw = {"prescale": [pow(pt, -1, q) for q in moduli[:lin]], "dec_mask": 1}
         lib = ab.lib()
         for _ in range(2):
-            she.mulKeySwitch(plan, a, b, hint, lh, lout)
+            she.mulKeySwitch(plan, a, b, hint, lh, lout, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.ab_kernel_launches()
         torch.cuda.synchronize()
         e0.record()
         for _ in range(iters):
-            she.mulKeySwitch(plan, a, b, hint, lh, lout)
+            she.mulKeySwitch(plan, a, b, hint, lh, lout, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters

@@ -134,14 +134,19 @@ int ab_rescale_drop_dev(const ab_plan *p, int64_t *out, const int64_t *in, int64
  * Eval.hs:65-67 `mul_ = pureE (*)`. */
 int ab_ct_mul_dev(const ab_plan *p, int64_t *out3, const int64_t *a2, const int64_t *b2, int64_t batch, int32_t nlimbs, void *stream);
 
-/* modSwitch = rescaleCyc Pow on every coefficient (Eval.hs:130), from the first `from_limbs` moduli to
- * the first `to_limbs` moduli of the plan.  to < from: drop limbs from the end, one at a time
- * (crtInv of the dropped limb, centred lift, CRT into the kept limbs, subtract, scale);
- * to > from: multiply by the new moduli and append zero limbs.  `npoly` polynomials per ciphertext.
+/* modSwitch = rescaleCyc on every coefficient of an MSD ciphertext (Eval.hs:130), from the first `from_limbs` moduli to
+ * the first `to_limbs` moduli of the plan.  to < from: drop limbs from the end (crtInv of the dropped limbs, centred lift,
+ * CRT into the kept limbs, subtract, scale; the result equals dropping them one at a time);
+ * to > from: multiply by the new moduli and append zero limbs.  `npoly` polynomials per ciphertext (<= 31).
+ * `dec_mask`: bit i set = polynomial i is rounded in the DECODING basis (rescaleDec), clear = in the powerful basis (rescalePow).
+ *   AB_RESCALE_POW (0) rounds every polynomial in the powerful basis; AB_RESCALE_LOL_LINEAR (1) is Lol's rescaleLinearMSD
+ *   [RECALL]: c0 through rescaleDec, every further coefficient through rescalePow.  Rings without odd primes have Dec = Pow.
+ * The caller brings the ciphertext to MSD form first (toMSD: ab_scalar_mul_dev by p^-1 mod q_l) -- see ab_mul_key_switch_dev.
  * `work`: device scratch of ab_mod_switch_work_bytes() bytes. */
+enum { AB_RESCALE_POW = 0, AB_RESCALE_LOL_LINEAR = 1 };
 int64_t ab_mod_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t npoly, int32_t from_limbs, int32_t to_limbs);
 int ab_mod_switch_dev(const ab_plan *p, int64_t *out, const int64_t *in, int64_t batch, int32_t npoly,
-                      int32_t from_limbs, int32_t to_limbs, void *work, void *stream);
+                      int32_t from_limbs, int32_t to_limbs, uint32_t dec_mask, void *work, void *stream);
 
 /* keySwitchQuadCirc (Eval.hs:133): (c0,c1,c2) -> (c0,c1) + sum_d reduce(decompose(c2))_d * hint_d.
  * `hint`: [gadget_len][2][nlimbs][n] in the CRT basis, shared by the whole batch. */
@@ -150,12 +155,18 @@ int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int64_t *in3, 
                            int64_t batch, int32_t nlimbs, int32_t base, void *work, void *stream);
 
 /* PT2CT `mul_` (PT2CT.hs:172-177) as one call:  modSwitch(l_out) . keySwitchQuad hint . modSwitch(l_hint) . (*)
- * a2, b2: [batch][2][l_in][n]; hint: [gadget_len(l_hint)][2][l_hint][n]; out2: [batch][2][l_out][n].
+ * a2, b2: [batch][2][l_in][n] (LSD forms); hint: [gadget_len(l_hint)][2][l_hint][n]; out2: [batch][2][l_out][n] (MSD form).
+ * `prescale`: HOST array of l_in residues or NULL.  Lol's (*) yields an LSD ciphertext and modSwitch begins with toMSD, which
+ *   multiplies every polynomial by p^-1 mod q_l (ModSwitchCtx_ = (RescaleCyc, ToSDCtx), Eval.hs:124): pass prescale[l] = p^-1 mod q_l
+ *   to get exactly  modSwitch . keySwitchQuadCirc . modSwitch . (*)  of Lol; it is folded into the product at no cost.  NULL = 1.
+ *   The (k, l) bookkeeping of the result (k = k_a + k_b + 1, l = l_a l_b (-Q_in) mod p) stays with the caller.
+ * `dec_mask`: rounding bases of both modSwitch steps, as in ab_mod_switch_dev.
  * Power-of-two rings that fit shared memory (examples/Arithmetic.hs: m' = 512) with TrivGad run as a single
  * kernel, every intermediate on chip; all other cases as the sequence of the entries above. */
 int64_t ab_mul_key_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t l_in, int32_t l_hint, int32_t l_out, int32_t base);
 int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
-                          int32_t l_in, int32_t l_hint, int32_t l_out, int32_t base, void *work, void *stream);
+                          int32_t l_in, int32_t l_hint, int32_t l_out, int32_t base, const int64_t *prescale, uint32_t dec_mask,
+                          void *work, void *stream);
 
 /* tunnel (Eval.hs:134): ring switch O_r' -> O_s' through E' = O_e'.
  *   c0' = sum_k embed(coeffsDec(c0)_k) * flin_k            (evalLin of the E'-linear function)
@@ -195,6 +206,10 @@ int ab_lift_plain_dev(const ab_plan *p, int64_t *out, const int64_t *in, int64_t
 
 /* ---- randomness for keys and hints (KeysHints.hs:96,113,115-129; upstream: Haskell MonadRandom + tGaussianDec) --
  * Counter-based (Philox4x32-10): every value is a function of (seed, stream_id, position) only.
+ * FOR TESTS AND BENCHMARKS: Philox is a statistical generator with a 64-bit key, not a CSPRNG, and a repeated (seed, stream_id)
+ * repeats its output -- callers must give every use its own stream_id (the host mirror folds a per-call nonce into it).  The error
+ * coefficients are i.i.d. in the decoding basis, NOT Lol's tGaussianDec (spherical in the canonical embedding): for m that is not a
+ * power of two the two distributions differ.  Production keys: draw masks and noise elsewhere and pass them to the entries above.
  *   ab_uniform_dev : out[b][l][j] uniform in [0, q_l)
  *   ab_gaussian_dev: out[b][j] signed integers, |x| = #{k : cdt[k] <= u} for a uniform 64-bit u, with
  *                    cdt[k] = floor(2^64 P(|X| <= k)) (HOST array, non-decreasing, at most 128 entries) */
@@ -202,7 +217,7 @@ int ab_uniform_dev(const ab_plan *p, int64_t *out, int64_t batch, int32_t nlimbs
 int ab_gaussian_dev(const ab_plan *p, int64_t *out, int64_t batch, const uint64_t *cdt, int32_t cdt_len, uint64_t seed, uint32_t stream_id, void *stream);
 
 /* ---- wire / on-disk format (upstream: none -- keys and hints are in-memory Dynamics, KeysHints.hs:36-39) -------------
- * 136-byte little-endian header, then one uint32 per residue in the device layout [batch][npoly][nlimbs][n]
+ * 136-byte little-endian header (format version 2), then one uint32 per residue in the device layout [batch][npoly][nlimbs][n]
  * (residues are below 2^31: half the bytes of the int64 tensors on NVLink / PCIe / disk). */
 typedef struct {
     uint32_t magic;            /* "AB2W"; filled in by ab_wire_pack_dev */
@@ -212,10 +227,13 @@ typedef struct {
     int32_t enc, k;            /* SymmSHE bookkeeping of ciphertexts: 0 LSD / 1 MSD, power of g */
     int64_t l, pmod;           /* scalar l, plaintext modulus */
     int64_t moduli[8];
-    uint64_t checksum;         /* sum of all residues mod 2^64; filled in by ab_wire_pack_dev, verified by ab_wire_unpack_dev */
+    uint64_t checksum;         /* sum_j (j+1) K w_j + sum_i (i+1) v_i mod 2^64 over the sixteen 64-bit header words w_j before this field
+                                  (K = 0x9E3779B97F4A7C15) and the payload words v_i: covers every header field and the ORDER of the
+                                  payload; filled in by ab_wire_pack_dev, verified by ab_wire_unpack_dev */
 } ab_wire_header;
 int64_t ab_wire_bytes(const ab_wire_header *h);                    /* header + payload */
-/* wire_dev: DEVICE buffer of ab_wire_bytes(h) bytes, 8-byte aligned; h: HOST header (magic/version/checksum are overwritten) */
+/* wire_dev: DEVICE buffer of ab_wire_bytes(h) bytes, 8-byte aligned; h: HOST header (magic/version/checksum are overwritten).
+ * Fails with AB_ERR_ARG if any value of data_dev is not a 31-bit residue (negative or >= 2^31); returns after the header is written. */
 int ab_wire_pack_dev(void *wire_dev, const ab_wire_header *h, const int64_t *data_dev, void *stream);
 /* validates magic, version and that wire_bytes matches the header; synchronous */
 int ab_wire_read_header(ab_wire_header *h_out, const void *wire_dev, int64_t wire_bytes);

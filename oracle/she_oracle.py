@@ -115,8 +115,10 @@ def ct_mul(m, moduli, a, b):
     return np.stack([c0 * g % qv, c1 * g % qv, c2 * g % qv], axis=1)
 
 
-def mod_switch(m, moduli, c, to):
-    """c[B, P, from, n] in the CRT basis -> [B, P, to, n] in the CRT basis (rescaleCyc Pow on every coefficient)"""
+def mod_switch(m, moduli, c, to, dec_mask=0):
+    """c[B, P, from, n] in the CRT basis -> [B, P, to, n] in the CRT basis: rescaleCyc on every coefficient, polynomial i rounded in
+    the decoding basis when bit i of dec_mask is set (Lol rescaleLinearMSD [RECALL]: c0 rescaleDec, c1 rescalePow -> dec_mask 1),
+    else in the powerful basis."""
     frm = c.shape[-2]
     if to == frm:
         return c.copy()
@@ -129,8 +131,13 @@ def mod_switch(m, moduli, c, to):
             out[..., k, :] = c[..., k, :] * s % moduli[k]
         return out
     x = crt_inv(m, moduli[:frm], c)
+    dec = [i for i in range(c.shape[1]) if (dec_mask >> i) & 1]
+    for i in dec:
+        x[:, i] = per_limb(O.l_inv, m, moduli[:frm], x[:, i])
     for L in range(frm, to, -1):
         x = rescale_drop(x, moduli[:L], L - 1)
+    for i in dec:
+        x[:, i] = per_limb(O.l, m, moduli[:to], x[:, i])
     return crt(m, moduli[:to], x)
 
 

@@ -18,6 +18,9 @@ Conventions fixed here ([RECALL]; each would have to be checked against lol-apps
   S6  (+) aligns encodings (to LSD), g-powers (mulG on the smaller k) and scalars (multiply by lift(l_b / l_a)).
   S7  modSwitch and keySwitchQuadCirc act on MSD forms; the key-switch hint satisfies
       h0_d + h1_d s = gamma_d s^2 + p e_d.
+  S8  modSwitch rounds c0 in the decoding basis and every further coefficient in the powerful basis (Lol rescaleLinearMSD:
+      rescaleDec c0, rescalePow c1; extended to the degree-2 ciphertext PT2CT.hs:177 rescales before the key switch).
+      gadget decomposition of c2 (key switch) and of the E'-coefficients of c1 (tunnel) is taken in the powerful basis.
 """
 from math import prod
 
@@ -48,6 +51,8 @@ def lift_plain(x, moduli, pmod):
 
 
 class SymmSHE:
+    rescale_dec_mask = 1      # S8: modSwitch rounds c0 in the decoding basis, every further coefficient in the powerful basis
+
     def __init__(self, m, mp, moduli, p):
         self.m, self.mp, self.moduli, self.p = m, mp, [int(q) for q in moduli], int(p)
         self.n, self.np_ = O.totient(O.factor(m)), O.totient(O.factor(mp))
@@ -170,7 +175,7 @@ class SymmSHE:
 
     def mod_switch(self, ct, to):
         ct = self.to_msd(ct)
-        return CT(S.mod_switch(self.mp, self.moduli, ct.c, to), ct.k, ct.l, "MSD")
+        return CT(S.mod_switch(self.mp, self.moduli, ct.c, to, self.rescale_dec_mask), ct.k, ct.l, "MSD")
 
     def key_switch_quad(self, ct, hint, base=0):
         ct = self.to_msd(ct)

@@ -87,24 +87,34 @@ def test_mul_keyswitch_pipeline(m, moduli, lin, lh, lout, base):
     c3 = she.ctMul(plan, dev(a), dev(b))
     w3 = S.ct_mul(m, moduli[:lin], a, b)
     assert (c3.cpu().numpy() == w3).all()
-    c3h = she.modSwitch(plan, c3, lh)
-    w3h = S.mod_switch(m, moduli, w3, lh)
-    assert (c3h.cpu().numpy() == w3h).all()
-    c2 = she.keySwitchQuadCirc(plan, c3h, dev(hint), base)
-    w2 = S.key_switch_quad(m, moduli, w3h, hint, base)
-    assert (c2.cpu().numpy() == w2).all()
-    out = she.modSwitch(plan, c2, lout)
-    want = S.mod_switch(m, moduli, w2, lout)
-    assert (out.cpu().numpy() == want).all()
-    # and the fused host call gives the same thing
-    assert (she.mulKeySwitch(plan, dev(a), dev(b), dev(hint), lh, lout, base).cpu().numpy() == want).all()
+    # dec_mask 0: every polynomial rounded in the powerful basis, inputs taken as they are; dec_mask 1 with the toMSD scalars of a
+    # plaintext modulus p = 7: Lol's modSwitch . keySwitchQuadCirc . modSwitch . (*) (c0 through the decoding basis)
+    for dec_mask, pre in ((0, None), (1, [pow(7, -1, q) for q in moduli[:lin]])):
+        w3m, c3m = w3, c3
+        if pre is not None:
+            w3m = w3 * np.array(pre, dtype=np.int64)[None, None, :, None] % np.array(moduli[:lin], dtype=np.int64)[None, None, :, None]
+            c3m = c3.clone()
+            ab.GT.scalarMul(plan, c3m.reshape(B * 3, lin, n), pre, nlimbs=lin)
+        c3h = she.modSwitch(plan, c3m, lh, dec_mask)
+        w3h = S.mod_switch(m, moduli, w3m, lh, dec_mask)
+        assert (c3h.cpu().numpy() == w3h).all()
+        c2 = she.keySwitchQuadCirc(plan, c3h, dev(hint), base)
+        w2 = S.key_switch_quad(m, moduli, w3h, hint, base)
+        assert (c2.cpu().numpy() == w2).all()
+        out = she.modSwitch(plan, c2, lout, dec_mask)
+        want = S.mod_switch(m, moduli, w2, lout, dec_mask)
+        assert (out.cpu().numpy() == want).all()
+        # and the one-call entry gives the same thing
+        assert (she.mulKeySwitch(plan, dev(a), dev(b), dev(hint), lh, lout, base, prescale=pre, dec_mask=dec_mask).cpu().numpy() == want).all()
 
 
 @pytest.mark.parametrize("m,moduli,frm,to", [(512, ARITH_Q, 3, 1), (512, ARITH_Q, 1, 3), (20475, RLWR_Q, 6, 2), (20475, RLWR_Q, 5, 5),
                                               (45, [181, 541, 631], 3, 2), (11648, TUNNEL_Q, 2, 1),
                                               # several limbs dropped in one rescale (Garner digits in the load phase of the transform)
                                               (20475, RLWR_Q, 5, 3), (20475, RLWR_Q, 6, 1), (45, [181, 541, 631], 3, 1), (43680, RLWR_Q, 6, 3),
-                                              (11648, TUNNEL_Q, 5, 2), (36, [37, 73, 109], 3, 1)])
+                                              (11648, TUNNEL_Q, 5, 2), (36, [37, 73, 109], 3, 1),
+                                              # a prime above 13: outside the shared-memory kernel, launch sequence with one pass per polynomial
+                                              (51, [103, 307, 409], 3, 1), (51, [103, 307, 409], 2, 1)])
 def test_mod_switch(m, moduli, frm, to):
     import alchemy_b200 as ab
     from alchemy_b200 import she
@@ -114,12 +124,18 @@ def test_mod_switch(m, moduli, frm, to):
     c[0, :, :, 0] = np.array(moduli[:frm]) - 1
     got = she.modSwitch(plan, dev(c), to).cpu().numpy()
     assert (got == S.mod_switch(m, moduli, c, to)).all()
+    # rounding bases per polynomial: c0 in the decoding basis (Lol rescaleLinearMSD), c1, both; a degree-2 ciphertext with c0 and c2
+    for dec_mask in (1, 2, 3):
+        assert (she.modSwitch(plan, dev(c), to, dec_mask).cpu().numpy() == S.mod_switch(m, moduli, c, to, dec_mask)).all(), dec_mask
+    c3 = rand(rng, (3, 3), moduli[:frm], plan.n)
+    for dec_mask in (1, 5):
+        assert (she.modSwitch(plan, dev(c3), to, dec_mask).cpu().numpy() == S.mod_switch(m, moduli, c3, to, dec_mask)).all(), dec_mask
     if frm == to:       # the host mirror returns its input for equal moduli; the ABI entry itself copies
         import ctypes as C
 
         import torch
         cd, out = dev(c), torch.zeros((4, 2, to, plan.n), dtype=torch.int64, device="cuda")
-        ab.check(ab.lib().ab_mod_switch_dev(plan.h, C.c_void_p(out.data_ptr()), C.c_void_p(cd.data_ptr()), 4, 2, frm, to, None, None))
+        ab.check(ab.lib().ab_mod_switch_dev(plan.h, C.c_void_p(out.data_ptr()), C.c_void_p(cd.data_ptr()), 4, 2, frm, to, 1, None, None))
         assert torch.equal(out, cd)
 
 
@@ -194,15 +210,15 @@ def test_empty_batches_and_bad_arguments_of_the_fused_entries():
     plan = ab.Plan(45, [181, 541, 631])
     z = torch.zeros(8, dtype=torch.int64, device="cuda")
     p = C.c_void_p(z.data_ptr())
-    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 0, 2, 3, 1, 0, None, None) == 0
+    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 0, 2, 3, 1, 0, None, 0, None, None) == 0
     assert lib.ab_ct_phase_dev(plan.h, p, p, p, 0, 2, 2, None) == 0
     assert lib.ab_rns_lift_reduce_dev(plan.h, p, None, p, 0, 2, 7, None) == 0
     assert lib.ab_lift_plain_dev(plan.h, p, p, 0, 2, 7, None) == 0
     assert lib.ab_ct_add_public_dev(plan.h, p, p, 0, 2, 2, None) == 0 and lib.ab_ct_mul_public_dev(plan.h, p, p, 0, 2, 2, None) == 0
     assert lib.ab_uniform_dev(plan.h, p, 0, 2, 1, 0, None) == 0
-    assert lib.ab_mul_key_switch_dev(plan.h, None, p, p, p, 1, 2, 3, 1, 0, p, None) == ab._lib.AB_ERR_ARG
-    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 1, 2, 4, 1, 0, p, None) == ab._lib.AB_ERR_ARG          # 4 limbs > plan
-    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 1, 2, 3, 1, 0, None, None) == ab._lib.AB_ERR_ARG       # scratch missing
+    assert lib.ab_mul_key_switch_dev(plan.h, None, p, p, p, 1, 2, 3, 1, 0, None, 0, p, None) == ab._lib.AB_ERR_ARG
+    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 1, 2, 4, 1, 0, None, 0, p, None) == ab._lib.AB_ERR_ARG          # 4 limbs > plan
+    assert lib.ab_mul_key_switch_dev(plan.h, p, p, p, p, 1, 2, 3, 1, 0, None, 0, None, None) == ab._lib.AB_ERR_ARG       # scratch missing
     assert lib.ab_rns_lift_reduce_dev(plan.h, p, None, p, 1, 2, 1, None) == ab._lib.AB_ERR_ARG                  # modulus 1
     assert lib.ab_gaussian_dev(plan.h, p, 1, None, 4, 1, 0, None) == ab._lib.AB_ERR_ARG
     assert lib.ab_mul_key_switch_work_bytes(plan.h, 4, 2, 3, 1, 0) > 0 and lib.ab_mul_key_switch_work_bytes(plan.h, 4, 2, 9, 1, 0) == -1
@@ -216,7 +232,7 @@ def test_empty_batches_and_bad_arguments_of_the_fused_entries():
         ab.GT.divGPow(p9, y)
 
 
-@pytest.mark.parametrize("switch", ["AB_NO_MAC=1", "AB_NO_BITS=1", "AB_NO_MULTIDROP=1", "AB_NO_MULKS=1", "AB_MX_MAC_PARTS=5", "AB_MX_T=128", "AB_MX_MAC_T=256",
+@pytest.mark.parametrize("switch", ["AB_NO_FUSE=1", "AB_NO_MAC=1", "AB_NO_BITS=1", "AB_NO_MULTIDROP=1", "AB_NO_MULKS=1", "AB_MX_MAC_PARTS=5", "AB_MX_T=128", "AB_MX_MAC_T=256",
                                     "AB_NO_SUBRING=1", "AB_MX_MAC_GROUP=1", "AB_MX_MAC_GROUP=3"])
 def test_every_kernel_variant_computes_the_same_bits(switch):
     """the A/B switches of DESIGN.md section 5 select alternative kernels / launch sequences; each must pass the same parity tests

@@ -70,6 +70,9 @@ def test_arithmetic_circuit_stage_by_stage(m, mp, moduli, p, lin, lh, lout, base
         po, pg = step_o(po), step_g(pg)
         assert same(pg.c, po.c) and (pg.k, pg.l, pg.enc) == (po.k, po.l, po.enc)
     assert tuple(pg.c.shape[1:3]) == (2, lout)
+    # the one-call pipeline (ab_mul_key_switch_dev with the toMSD scalars folded into the product) is Lol's sequence, bit for bit
+    fg = gpu.mulKeySwitch(sg, yg, hint_g, lh, lout, base)
+    assert same(fg.c, po.c) and (fg.k, fg.l, fg.enc) == (po.k, po.l, po.enc)
     got = gpu.decrypt(sk_g, pg)
     assert same(got, ora.decrypt(sk_o, po)) and same(got, want)        # the reference's PASS criterion
     rate_g, rate_o = gpu.errorRate(sk_g, pg).cpu().numpy(), ora.error_rate(sk_o, po)
@@ -121,6 +124,38 @@ def test_mod_switch_pt_and_rns_lift_edges():
             ab.check(ab.lib().ab_rns_lift_reduce_dev(plan.h, C.c_void_p(out.data_ptr()), C.c_void_p(rate.data_ptr()), C.c_void_p(dev(x).data_ptr()), 1, L, pmod, None))
             assert out.cpu().numpy()[0].tolist() == [v % pmod for v in vals]
             assert abs(rate.item() - max(abs(v) for v in vals) / Q) < 1e-12
+
+
+def test_error_rate_of_small_negative_terms_at_six_limbs_and_large_batches():
+    """errorRate_ (Eval.hs:155-160) at ALCHEMY's real moduli: Q = 2^180, error terms of a few units, so rates near 1e-54.  A negative
+    term must report |x| / Q to double precision (not 1 - x/Q, which bottoms out at 1e-16); more than 65535 ring elements in one call."""
+    import ctypes as C
+
+    import torch
+
+    import alchemy_b200 as ab
+    plan = ab.Plan(20475, RLWR_Q[:6])
+    n, rng = plan.n, np.random.default_rng(5)
+    for L in (4, 6):
+        q = RLWR_Q[:L]
+        Q = int(np.prod([int(v) for v in q], dtype=object))
+        rows = [[-3] + [0] * (n - 1), [2, -7] + [1] * (n - 2), [-(1 << 70)] + [5] * (n - 1), [int(v) for v in rng.integers(-50, 51, size=n)]]
+        x = np.array([[[v % ql for v in row] for ql in q] for row in rows], dtype=np.int64)
+        out = torch.empty((len(rows), n), dtype=torch.int64, device="cuda")
+        rate = torch.zeros(len(rows), dtype=torch.float64, device="cuda")
+        ab.check(ab.lib().ab_rns_lift_reduce_dev(plan.h, C.c_void_p(out.data_ptr()), C.c_void_p(rate.data_ptr()), C.c_void_p(dev(x).data_ptr()), len(rows), L, 32, None))
+        assert out.cpu().numpy().tolist() == [[v % 32 for v in row] for row in rows]
+        want = np.array([max(abs(v) for v in row) / Q for row in rows])
+        assert np.allclose(rate.cpu().numpy(), want, rtol=1e-12, atol=0), (rate.cpu().numpy(), want)
+    small = ab.Plan(16, primes_1_mod(16, 1 << 22, 2))
+    B, q = 70000, primes_1_mod(16, 1 << 22, 2)
+    vals = rng.integers(-1000, 1001, size=(B, small.n))
+    x = np.stack([np.mod(vals, ql) for ql in q], axis=1)
+    out = torch.empty((B, small.n), dtype=torch.int64, device="cuda")
+    rate = torch.zeros(B, dtype=torch.float64, device="cuda")
+    ab.check(ab.lib().ab_rns_lift_reduce_dev(small.h, C.c_void_p(out.data_ptr()), C.c_void_p(rate.data_ptr()), C.c_void_p(dev(x).data_ptr()), B, 2, 7, None))
+    assert (out.cpu().numpy() == np.mod(vals, 7)).all()
+    assert np.allclose(rate.cpu().numpy(), np.abs(vals).max(axis=1) / float(q[0] * q[1]), rtol=1e-12, atol=0)
 
 
 def test_device_randomness_matches_the_cpu_restatement_and_drives_the_circuit():

@@ -169,6 +169,34 @@ def test_mod_switch_scales_the_phase():
     assert (S.mod_switch(m, moduli, c, 1) == c).all()
 
 
+def test_mod_switch_rounds_each_polynomial_in_the_basis_its_mask_bit_names():
+    """dec_mask of S.mod_switch (Lol rescaleLinearMSD: c0 through rescaleDec, c1 through rescalePow): in the chosen basis every
+    coefficient of the result is the input coefficient divided by the dropped moduli, off by at most half a unit per dropped limb;
+    on a ring with odd primes the two bases give different ciphertexts."""
+    m, n = 45, 24
+    moduli = primes_1_mod(m, 1 << 24, 3)
+    rng = np.random.default_rng(9)
+    c = np.stack([rng.integers(0, qq, size=(3, 2, n)) for qq in moduli], axis=2)
+    outs = {}
+    for dec_mask in (0, 1, 2, 3):
+        for to in (2, 1):
+            out = S.mod_switch(m, moduli, c, to, dec_mask)
+            outs[(dec_mask, to)] = out
+            qt, dropped = moduli[:to], prod(moduli[to:])
+            x_in, x_out = S.crt_inv(m, moduli, c), S.crt_inv(m, qt, out)
+            for i in range(2):
+                a, b = x_in[:, i], x_out[:, i]
+                if (dec_mask >> i) & 1:
+                    a, b = S.per_limb(O.l_inv, m, moduli, a), S.per_limb(O.l_inv, m, qt, b)
+                X, Q = crt_lift(a.transpose(1, 0, 2), moduli)
+                Y, Qt = crt_lift(b.transpose(1, 0, 2), qt)
+                d = (Y * dropped - X) % Q
+                d = np.where(d * 2 >= Q, d - Q, d)
+                assert (2 * abs(d) <= dropped * (3 - to)).all(), (dec_mask, to, i)
+    assert (outs[(1, 1)][:, 1] == outs[(0, 1)][:, 1]).all() and (outs[(1, 1)][:, 0] != outs[(0, 1)][:, 0]).any()
+    assert (outs[(2, 1)][:, 0] == outs[(0, 1)][:, 0]).all() and (outs[(3, 1)][:, 0] == outs[(1, 1)][:, 0]).all()
+
+
 TUNNELS = [(12, 4, 20), (8, 4, 24), (9, 3, 21), (28, 4, 12), (45, 15, 15), (16, 16, 48)]
 
 

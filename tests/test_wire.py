@@ -50,6 +50,22 @@ def test_pack_unpack_files_and_corruption(tmp_path):
         wire.unpack(bad)
     with pytest.raises(ab.AlchemyError, match="truncated"):
         wire.unpack(w[:-4].clone())
+    # two payload words exchanged (a plain sum would not notice), and a flipped bookkeeping field of the header (k: 1 -> 3)
+    swapped = w.clone()
+    swapped[136:140], swapped[140:144] = w[140:144].clone(), w[136:140].clone()
+    with pytest.raises(ab.AlchemyError, match="checksum"):
+        wire.unpack(swapped)
+    for off in (44, 48, 64):                 # k, l, first modulus
+        flipped = w.clone()
+        flipped[off] ^= 2
+        with pytest.raises(ab.AlchemyError, match="checksum"):
+            wire.unpack(flipped)
+    # values that are not 31-bit residues are refused by the packer instead of being truncated
+    for badval in (-1, 1 << 31, 1 << 40):
+        y = xd.clone()
+        y[1, 2, 1, 77] = badval
+        with pytest.raises(ab.AlchemyError, match="residue"):
+            wire.pack("ciphertexts", 20475, y, moduli)
     nope = w.clone()
     nope[0] = 0
     with pytest.raises(ab.AlchemyError, match="not an alchemy_b200 wire"):

@@ -50,7 +50,8 @@ def mul_cases(iters):
         n = plan.n
         a, b, hint = rnd(moduli[:lin], (B, 2), n), rnd(moduli[:lin], (B, 2), n), rnd(moduli[:lh], (lh, 2), n)
         l0 = ab.lib().ab_kernel_launches()
-        ms = timeit(lambda: she.mulKeySwitch(plan, a, b, hint, lh, lout), iters)
+        kw = {"prescale": [pow(7 if m == 512 else 32, -1, q) for q in moduli[:lin]], "dec_mask": 1}     # Lol: toMSD scalars, c0 rounded in Dec
+        ms = timeit(lambda: she.mulKeySwitch(plan, a, b, hint, lh, lout, **kw), iters)
         nbytes = (32 * n * lin + 16 * n * lout) * B
         out.append({"case": name, "m": m, "n": n, "L_in": lin, "L_hint": lh, "L_out": lout, "B": B, "ms": ms, "ops_per_s": B / (ms * 1e-3),
                     "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / PEAK,
@@ -81,10 +82,10 @@ def tunnel_chain(total, iters, rank, world):
     x = rnd(q, (B, 2), plans[11648].n)
 
     def run():
-        c = she.modSwitch(plans[11648], x, 1)
+        c = she.modSwitch(plans[11648], x, 1, 1)
         for i, (r, e, s) in enumerate(hops):
             c = tn[i](c, flin[i], hint[i], base=2)
-            c = she.modSwitch(plans[s], c, 1)       # equal moduli: the identity rescale of Lol
+            c = she.modSwitch(plans[s], c, 1, 1)       # equal moduli: the identity rescale of Lol
         return c
     l0 = ab.lib().ab_kernel_launches()
     ms = timeit(run, iters)
@@ -131,9 +132,9 @@ def rlwr_chain(B, iters):
         c = x0.clone()
         ab.check(lib.ab_ct_mul_public_dev(plans[11648].h, ptr(c), ptr(pub), B, 2, 5, st()))
         for t, s, lh, lout, flin, hint in hops:
-            c = she.modSwitch(t.r, c, lh)
+            c = she.modSwitch(t.r, c, lh, 1)
             c = t(c, flin, hint, base=0)
-            c = she.modSwitch(plans[s], c, lout)
+            c = she.modSwitch(plans[s], c, lout, 1)
         # rescaling tree: level k consumes pairs of level k-1 results; synthetic operands of the right shape per level
         cur = c                                                      # [B, 2, 4, n5]
         for (lin, lh, lout, count), hint, pb in zip(levels, hints, pub5):
@@ -142,7 +143,7 @@ def rlwr_chain(B, iters):
             for _ in range(count):
                 b = a.clone()
                 ab.check(lib.ab_ct_add_public_dev(p5.h, ptr(b), ptr(pb), B, 2, lin, st()))      # the (z_i + y) leaves / node operands
-                outs.append(she.mulKeySwitch(p5, a, b, hint, lh, lout))
+                outs.append(she.mulKeySwitch(p5, a, b, hint, lh, lout, prescale=[pow(32, -1, q) for q in Q[:lin]], dec_mask=1))
             cur = outs[0]
         return cur
     l0 = lib.ab_kernel_launches()
