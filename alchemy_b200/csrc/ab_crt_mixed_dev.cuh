@@ -171,6 +171,150 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
     }
 }
 
+// ---- CRT_p of a prime axis through its conjugate symmetry (step kind 2; tables: ab_mixed_plan.cpp push_pair_tables) ----------------
+// Forward: u_j = x_j + x_(p-j), v_j = x_j - x_(p-j) (x_(p-1) = 0), out_i / out_(p-i) = x_0 + sum_j u_j C_ij +/- sum_j v_j S_ij.
+// Inverse: U_k = X_k + X_(p-k), V_k = X_k - X_(p-k), y_j / y_(p-j) = sum_k U_k C'_jk -/+ sum_k V_k S'_jk, y_0 = sum_k U_k / p,
+// x_j = y_j - y_(p-1).  P = p - 1 inputs and outputs, h = P / 2 products per 64-bit sum, two sums per pair of outputs: half the
+// IMAD.WIDE of the dense step.  The sums u, v stay unreduced (below 2q): narrow T < P q^2 as in the dense step; WIDE splits them
+// into 16-bit halves against the two constant sets (terms below 2^47).
+template <int H, int V, bool WIDE>
+__device__ __forceinline__ void pair_dot(const uint4 *__restrict__ row, const uint32_t (*xa)[V], const uint32_t (*xb)[V], uint32_t q, uint32_t qinv_neg,
+                                         uint32_t (&a)[V], uint32_t (&b)[V]) {
+    // row: [A_1..A_H, B_1..B_H, pad] (and, WIDE, the same times 2^16); xa[j], xb[j] (j < H): the factors of the A and B constants
+    constexpr int PP = (2 * H + 3) & ~3;
+    uint32_t c[PP], ch[WIDE ? PP : 1];
+    mx_static_for<PP / 4>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        const uint4 t = row[k];
+        c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
+        if (WIDE) {
+            const uint4 u = row[PP / 4 + k];
+            ch[WIDE ? 4 * k : 0] = u.x; ch[WIDE ? 4 * k + 1 : 0] = u.y; ch[WIDE ? 4 * k + 2 : 0] = u.z; ch[WIDE ? 4 * k + 3 : 0] = u.w;
+        }
+    });
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        uint64_t sa = 0, sb = 0;
+        mx_static_for<H>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            if (WIDE) {
+                sa += (uint64_t)(xa[j][k] & 0xffffu) * c[j] + (uint64_t)(xa[j][k] >> 16) * ch[WIDE ? j : 0];
+                sb += (uint64_t)(xb[j][k] & 0xffffu) * c[H + j] + (uint64_t)(xb[j][k] >> 16) * ch[WIDE ? H + j : 0];
+            } else {
+                sa += (uint64_t)xa[j][k] * c[j];
+                sb += (uint64_t)xb[j][k] * c[H + j];
+            }
+        });
+        uint32_t ta = (uint32_t)((sa + (uint64_t)((uint32_t)sa * qinv_neg) * q) >> 32);
+        uint32_t tb = (uint32_t)((sb + (uint64_t)((uint32_t)sb * qinv_neg) * q) >> 32);
+        if (!WIDE && H > 2) { ta = ab_csub(ta, 2 * q); tb = ab_csub(tb, 2 * q); }
+        a[k] = ab_csub(ta, q);
+        b[k] = ab_csub(tb, q);
+    }
+}
+template <int P, int V, bool WIDE, bool INVS, bool CONTIG = false>
+__device__ __forceinline__ void pair_item(uint32_t *sm, const uint32_t *__restrict__ tab, const AbMxStep &s, int v, uint32_t q, uint32_t qinv_neg) {
+    static_assert(P % 2 == 0 && P >= 4, "pair steps are for odd primes p >= 5");
+    static_assert(!CONTIG || V == 1, "contiguous items have one column");
+    constexpr int H = P / 2, PP = (P + 3) & ~3, RW = WIDE ? 2 * PP : PP;
+    int tb, off;
+    item_coords<V>(s, v, tb, off);
+    const int es = s.estride;
+    uint32_t *e = sm + tb * (P * es) + off;
+    const uint4 *M = reinterpret_cast<const uint4 *>(tab + (WIDE ? s.tab_off_w : s.tab_off));
+    uint32_t x[P][V];
+    if (CONTIG) {
+        if (P % 4 == 0) {
+            mx_static_for<(P % 4 == 0 ? P / 4 : 0)>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                const uint4 t = reinterpret_cast<const uint4 *>(e)[k];
+                x[(4 * k) % P][0] = t.x; x[(4 * k + 1) % P][0] = t.y; x[(4 * k + 2) % P][0] = t.z; x[(4 * k + 3) % P][0] = t.w;
+            });
+        } else {
+            mx_static_for<P / 2>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                const uint2 t = reinterpret_cast<const uint2 *>(e)[k];
+                x[(2 * k) % P][0] = t.x; x[(2 * k + 1) % P][0] = t.y;
+            });
+        }
+    } else {
+        mx_static_for<P>([&](auto C) { ld_cols<V>(e + decltype(C)::value * es, x[decltype(C)::value]); });
+    }
+    uint32_t oo[CONTIG ? P : 1];
+    auto put = [&](int r, const uint32_t (&o)[V]) {
+        if (CONTIG) oo[CONTIG ? r : 0] = o[0];
+        else st_cols<V>(e + r * es, o);          // all inputs are already in registers: in place is safe
+    };
+    if (!INVS) {
+        // inputs x_0 .. x_(p-2); pairs (j, p-j) = positions (j, P+1-j) for j = 2..H; j = 1 has no partner (u_1 = v_1 = x_1)
+        uint32_t xa[H][V], xb[H][V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            xa[0][k] = x[1][k]; xb[0][k] = x[1][k];
+            mx_static_for<H - 1>([&](auto J) {
+                constexpr int j = decltype(J)::value + 2;
+                const uint32_t a = x[j][k], b = x[(P + 1 - j) % P][k];
+                xa[j - 1][k] = a + b;
+                xb[j - 1][k] = a - b + q;
+            });
+        }
+        mx_static_for<H>([&](auto I) {
+            constexpr int i = decltype(I)::value + 1;
+            uint32_t a[V], b[V], o0[V], o1[V];
+            pair_dot<H, V, WIDE>(M + (i - 1) * (RW / 4), xa, xb, q, qinv_neg, a, b);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const uint32_t t = ab_addmod(a[k], x[0][k], q);
+                o0[k] = ab_addmod(t, b[k], q);
+                o1[k] = ab_submod(t, b[k], q);
+            }
+            put(i - 1, o0);
+            put(P - i, o1);
+        });
+    } else {
+        // inputs X_1 .. X_(p-1) at positions 0 .. P-1; pairs (k, p-k) = positions (k-1, P-k)
+        uint32_t xa[H][V], xb[H][V];
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            mx_static_for<H>([&](auto J) {
+                constexpr int kk = decltype(J)::value + 1;
+                const uint32_t a = x[kk - 1][k], b = x[P - kk][k];
+                xa[kk - 1][k] = a + b;
+                xb[kk - 1][k] = a - b + q;
+            });
+        uint32_t y0[V], dummy[V], c[V];
+        pair_dot<H, V, WIDE>(M, xa, xb, q, qinv_neg, y0, dummy);      // row 0: (1/p, ..., 1/p | 0, ..., 0)
+        mx_static_for<H>([&](auto I) {
+            constexpr int j = decltype(I)::value + 1;
+            uint32_t a[V], b[V], o0[V], o1[V];
+            pair_dot<H, V, WIDE>(M + j * (RW / 4), xa, xb, q, qinv_neg, a, b);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const uint32_t ym = ab_submod(a[k], b[k], q), yp = ab_addmod(a[k], b[k], q);      // y_j, y_(p-j)
+                if (j == 1) { c[k] = yp; o0[k] = ab_submod(y0[k], c[k], q); }                    // y_(p-1); x_0 = y_0 - y_(p-1)
+                o1[k] = ab_submod(ym, c[k], q);                                                   // x_j
+                if (j > 1) o0[k] = ab_submod(yp, c[k], q);                                        // x_(p-j) at position P+1-j
+            }
+            if (j == 1) put(0, o0);
+            else put(P + 1 - j, o0);
+            put(j, o1);
+        });
+    }
+    if (CONTIG) {
+        if (P % 4 == 0) {
+            mx_static_for<(P % 4 == 0 ? P / 4 : 0)>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                reinterpret_cast<uint4 *>(e)[k] = make_uint4(oo[(4 * k) % P], oo[(4 * k + 1) % P], oo[(4 * k + 2) % P], oo[(4 * k + 3) % P]);
+            });
+        } else {
+            mx_static_for<P / 2>([&](auto K) {
+                constexpr int k = decltype(K)::value;
+                reinterpret_cast<uint2 *>(e)[k] = make_uint2(oo[(2 * k) % P], oo[(2 * k + 1) % P]);
+            });
+        }
+    }
+}
+
 // G radix-2 stages on 2^G residues (V columns); forward: Cooley-Tukey (twiddle the upper input), inverse:
 // Gentleman-Sande.  LAZY (q < 2^30): Harvey butterflies, values in [0,4q) / [0,2q); otherwise exact.
 template <int G, int V, bool INV, bool LAZY>
@@ -250,7 +394,20 @@ __device__ __forceinline__ void run_program(const MxArgs &args, uint32_t *sm, co
     for (int si = first_step; si < args.nsteps; ++si) {
         const AbMxStep &s = args.steps[si];
         const int nw = s.nwork / s.vec;
-        if (s.kind == 0) {
+        if (s.kind == 2) {
+#define AB_PR(P)                                                                                                    \
+    case P:                                                                                                         \
+        if (s.vec == 2) for (int v = threadIdx.x; v < nw; v += blockDim.x) pair_item<P, 2, WIDE, INV>(sm, tab, s, v, q, qinv_neg); \
+        else if (s.estride == 1 && contig_ok)                                                                       \
+            for (int v = threadIdx.x; v < nw; v += blockDim.x) pair_item<P, 1, WIDE, INV, true>(sm, tab, s, v, q, qinv_neg); \
+        else for (int v = threadIdx.x; v < nw; v += blockDim.x) pair_item<P, 1, WIDE, INV>(sm, tab, s, v, q, qinv_neg);      \
+        break;
+            switch (s.span) {
+                AB_PR(4) AB_PR(6) AB_PR(10) AB_PR(12)
+                default: break;
+            }
+#undef AB_PR
+        } else if (s.kind == 0) {
 #define AB_MV(P)                                                                                                    \
     case P:                                                                                                         \
         if (s.vec == 2) for (int v = threadIdx.x; v < nw; v += blockDim.x) matvec_item<P, 2, WIDE>(sm, tab, s, v, q, qinv_neg); \
@@ -505,7 +662,8 @@ static inline int pick_threads(const std::vector<AbMxStep> &steps, int n, size_t
         double time = 6.0 * ((n / 2 + T - 1) / T);                 // load + store phases
         for (const AbMxStep &s : steps) {
             const int items = s.nwork / s.vec, rounds = (items + T - 1) / T;
-            const double w = s.kind == 0 ? (double)s.span * s.vec * (s.span + 6) : (double)s.span * s.vec * (3.5 * s.g + 2);
+            const double w = s.kind == 0 ? (double)s.span * s.vec * (s.span + 6) : s.kind == 2 ? (double)s.span * s.vec * (s.span / 2 + 12)
+                                         : (double)s.span * s.vec * (3.5 * s.g + 2);
             time += rounds * w;
         }
         const double tput = ctas / time;

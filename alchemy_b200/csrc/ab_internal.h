@@ -134,7 +134,8 @@ struct AbGenStep {
 // in shared memory.  Work item v of a step: tb = v / estride, off = v % estride, base = tb*span*estride + off;
 // its `span` elements sit at base + k*estride.
 struct AbMxStep {
-    int32_t kind;        // 0 = dense span x span mat-vec (Montgomery constants), 1 = group of G radix-2 stages (Shoup twiddles)
+    int32_t kind;        // 0 = dense span x span mat-vec (Montgomery constants), 1 = group of G radix-2 stages (Shoup twiddles),
+                         // 2 = CRT_p of a prime axis (span = p - 1) through its conjugate symmetry: half the multiplications (ab_mixed_plan.cpp)
     int32_t span;        // mat-vec: P;  radix-2: 2^G
     int32_t g;           // radix-2: G (1..3)
     int32_t estride;

@@ -11,7 +11,15 @@
 //   * the inverse program is the reversed list with every matrix inverted mod q (Gauss-Jordan), so
 //     crtInv . crt = id holds by construction;
 //   * matrix constants are stored as c * 2^32 mod q: the kernel accumulates sum_c x_c * M_rc in 64 bits and
-//     does ONE Montgomery reduction per output instead of one modular reduction per term.
+//     does ONE Montgomery reduction per output instead of one modular reduction per term;
+//   * CRT_p of a prime axis p >= 5 (exponent 1: no twiddles folded in) runs as a PAIR step (kind 2).  With w = omega_p, rows i and
+//     p - i of the matrix w^(ij) are conjugate and so are columns j and p - j (the missing column p - 1 counts as a zero input):
+//         out_i, out_(p-i) = x_0 + sum_{j=1..h} u_j C_ij  +/-  sum_{j=1..h} v_j S_ij,      h = (p-1)/2,
+//         u_j = x_j + x_(p-j),  v_j = x_j - x_(p-j),  C_ij = (w^(ij) + w^(-ij)) / 2,  S_ij = (w^(ij) - w^(-ij)) / 2,
+//     i.e. p - 1 multiplications per pair of outputs instead of 2 (p - 1).  The inverse has the same shape:
+//         x_j = y_j - y_(p-1),   y_j, y_(p-j) = sum_k U_k C'_jk  -/+  sum_k V_k S'_jk,   U_k, V_k = X_k +/- X_(p-k),  C', S' = C, S / p,
+//     and y_0 = (sum_k U_k) / p.  64-bit multiply-accumulate (IMAD.WIDE) is the slowest multiply of the SM -- measured 23 lanes
+//     per clock per SM on B200 against 63 for a 32-bit IMAD (tools/micro/pipes.cu) -- and these steps were most of them.
 // For 2^30 <= q < 2^31 the 64-bit sum of full products would overflow: those limbs get a "wide" table with two
 // constants per entry (M 2^32 and M 2^48 mod q) and the kernel splits x into 16-bit halves, so every term is
 // below 2^47 and one reduction per output still suffices.
@@ -61,6 +69,35 @@ void push_matrices(Builder &B, int l, const std::vector<std::vector<uint64_t>> &
             if (B.mode[l] == 2)
                 for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < P ? (uint32_t)((to_mont(M[r * P + c], q) << 16) % q) : 0u);
         }
+}
+
+// tables of a pair step (kind 2) for the prime p with w = omega_p: row i = 1..h holds C_i1..C_ih, S_i1..S_ih (forward) or the same
+// divided by p (inverse, preceded by the row of y_0: h times 1/p, then zeros); Montgomery form, rows padded to 16 bytes; the wide
+// layout appends to every row its copy times 2^16.
+void push_pair_tables(Builder &B, int l, int p, uint64_t w, uint64_t q, bool inverse) {
+    const int P = p - 1, h = P / 2, PP = row_stride(P);
+    const uint64_t inv2 = invmod(2 % q, q), invp = invmod((uint64_t)p % q, q), winv = invmod(w, q);
+    auto emit_row = [&](const std::vector<uint64_t> &row) {
+        for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < (int)row.size() ? (uint32_t)to_mont(row[c], q) : 0u);
+        if (B.mode[l] == 2)
+            for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < (int)row.size() ? (uint32_t)((to_mont(row[c], q) << 16) % q) : 0u);
+    };
+    if (inverse) {
+        std::vector<uint64_t> row(P, 0);
+        for (int k = 0; k < h; ++k) row[k] = invp;
+        emit_row(row);
+    }
+    for (int i = 1; i <= h; ++i) {
+        std::vector<uint64_t> row(P);
+        for (int j = 1; j <= h; ++j) {
+            const uint64_t a = powmod(w, (uint64_t)i * j % p, q), b = powmod(winv, (uint64_t)i * j % p, q);
+            uint64_t c = mulmod((a + b) % q, inv2, q), sgn = mulmod((a + q - b) % q, inv2, q);
+            if (inverse) { c = mulmod(c, invp, q); sgn = mulmod(sgn, invp, q); }
+            row[j - 1] = c;
+            row[h + j - 1] = sgn;
+        }
+        emit_row(row);
+    }
 }
 
 std::vector<uint64_t> invert_matrix(std::vector<uint64_t> a, int P, uint64_t q) {
@@ -130,7 +167,13 @@ void ab_build_mixed(ab_plan *pl) {
     std::vector<int> mode(L);
     for (int l = 0; l < L; ++l) mode[l] = pl->q[l] < (1ll << 30) ? 1 : 2;
     Builder F(L, mode), I(L, mode);
-    struct Pending { AbMxStep step; std::vector<std::vector<std::vector<uint64_t>>> mats; };   // forward record, for inversion
+    struct Pending {
+        AbMxStep step;
+        std::vector<std::vector<std::vector<uint64_t>>> mats;   // forward record, for inversion
+        int sym_p = 0;                                             // kind 2: the prime
+        std::vector<uint64_t> sym_w;                               // kind 2: omega_p per limb
+    };
+    static const bool no_sym = getenv("AB_MX_NOSYM") && atoi(getenv("AB_MX_NOSYM")) != 0;      // A/B measurements only
     std::vector<Pending> recs;
 
     for (int ai = (int)pl->axes.size() - 1; ai >= 0; --ai) {
@@ -198,7 +241,9 @@ void ab_build_mixed(ab_plan *pl) {
                             M[r * P1 + c] = mulmod(powmod(wp, (r + 1) * c % p, q), powmod(wpp, rv * (r + 1) % pp, q), q);
                     rec.mats[l].push_back(M);
                 }
+                rec.sym_w.push_back(wp);
             }
+            if (e == 1 && p >= 5 && !no_sym) { rec.step.kind = 2; rec.sym_p = p; }
             recs.push_back(rec);
         }
         const int64_t ss = (p - 1) * rts;
@@ -225,7 +270,7 @@ void ab_build_mixed(ab_plan *pl) {
     // uniform matrix over contiguous items
     std::vector<std::vector<uint32_t>> bits_lut;
     int bits_p = 0, bits_h = 0;
-    if (!recs.empty() && recs[0].step.kind == 0 && recs[0].step.estride == 1 && recs[0].step.row_mode == 0 && recs[0].step.span <= 12 &&
+    if (!recs.empty() && (recs[0].step.kind == 0 || recs[0].step.kind == 2) && recs[0].step.estride == 1 && recs[0].step.row_mode == 0 && recs[0].step.span <= 12 &&
         recs[0].mats[0].size() == 1) {
         bits_p = recs[0].step.span; bits_h = (bits_p + 1) / 2;
         bits_lut.resize(L);
@@ -254,7 +299,8 @@ void ab_build_mixed(ab_plan *pl) {
         s.tab_off_w = B.off_w;
         for (int l = 0; l < L; ++l) {
             const uint64_t q = pl->q[l];
-            if (s.kind == 0) {
+            if (s.kind == 2) push_pair_tables(B, l, rec.sym_p, rec.sym_w[l], q, inverse);
+            else if (s.kind == 0) {
                 if (!inverse) push_matrices(B, l, rec.mats[l], s.span, q);
                 else {
                     std::vector<std::vector<uint64_t>> inv;
@@ -281,7 +327,11 @@ void ab_build_mixed(ab_plan *pl) {
                 B.tab[l].push_back(shoup(scale, q));
             }
         }
-        if (s.kind == 0) {
+        if (s.kind == 2) {
+            const int words = (s.span / 2 + (inverse ? 1 : 0)) * row_stride(s.span);      // h (+ 1: the y_0 row) rows of 2 h constants
+            B.off_n += words;
+            B.off_w += 2 * words;
+        } else if (s.kind == 0) {
             const int words = s.rows * s.span * row_stride(s.span);
             B.off_n += words;
             B.off_w += 2 * words;
@@ -333,7 +383,7 @@ void ab_build_mixed(ab_plan *pl) {
         bool ok = true;
         if (mode[l] == 1)
             for (auto &s : F.steps)
-                if (s.kind == 0) {
+                if (s.kind == 0 || s.kind == 2) {      // kind 2: span / 2 terms with a factor below 2 q each
                     ok = ok && ((unsigned __int128)s.span * (q - 1) * (q - 1) + (((unsigned __int128)1 << 32) - 1) * q < ((unsigned __int128)1 << 64));
                     ok = ok && ((unsigned __int128)s.span * q < ((unsigned __int128)3 << 32));
                 }
