@@ -65,20 +65,34 @@ __device__ __forceinline__ void st_cols(uint32_t *p, const uint32_t (&x)[V]) {
 
 // out = M x for V columns with one Montgomery reduction per output; x in [0,q), result in [0,q).
 // narrow (q < 2^30): T = sum x_c M'_c < P q^2, T + m q < 2^64, t < 4q.
-// WIDE  (q < 2^31): x = xh 2^16 + xl, T = sum xl_c M'_c + xh_c M''_c with M'' = M' 2^16: every term < 2^47.
+// WIDE  (q < 2^31): inputs and constants centred, T = sum x_c M_c as a signed 64-bit sum of products below q^2 / 4 (at most
+// seven per sum; the 10- to 12-point steps use two sums), one signed Montgomery reduction per sum.
 // CONTIG (V == 1, element stride 1: the steps of the last tensor axis): the P residues of an item are contiguous, so they
 // are moved with 16- or 8-byte shared-memory accesses.  With 4-byte accesses the lanes of a warp sit P words apart and,
 // for P = 12, four of them share every bank (measured: 70 % of all excess shared-memory wavefronts of the transform);
 // lanes reading 16 bytes at a 48-byte pitch cover the 32 banks exactly once per quarter warp.
+// signed helpers of the WIDE path (2^30 <= q < 2^31): centred inputs and constants, signed 64-bit sums
+__device__ __forceinline__ int32_t mx_centre(uint32_t x, uint32_t q, uint32_t hq) { return (int32_t)(x > hq ? x - q : x); }      // [0,q) -> [-hq, hq]
+// signed Montgomery: T 2^-32 mod q for |T| < 2^63, result in [0,q).  qinv = q^-1 mod 2^32 = -qinv_neg.  The low words of T and m q
+// agree, so (T - m q) / 2^32 = hi(T) - hi(m q) exactly; |t| <= |T| / 2^32 + q / 2 < 2^31 by the plan's bound check (t in (-2q, 2q)).
+__device__ __forceinline__ uint32_t mx_redc_s(int64_t T, uint32_t q, uint32_t qinv_neg) {
+    const int32_t m = (int32_t)((uint32_t)T * (0u - qinv_neg));
+    int32_t t = (int32_t)(T >> 32) - __mulhi(m, (int32_t)q);
+    t += (t >> 31) & (int32_t)q;
+    t += (t >> 31) & (int32_t)q;
+    return ab_csub((uint32_t)t, q);
+}
+
 template <int P, int V, bool WIDE, bool CONTIG = false>
 __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__restrict__ tab, const AbMxStep &s, int v, uint32_t q, uint32_t qinv_neg) {
     static_assert(!CONTIG || V == 1, "contiguous items have one column");
-    constexpr int PP = (P + 3) & ~3, RW = WIDE ? 2 * PP : PP;
+    constexpr int PP = (P + 3) & ~3;
+    constexpr int NA = (WIDE && P > 7) ? 2 : 1, PH = (P + NA - 1) / NA;     // WIDE: at most seven signed products per 64-bit sum
     int tb, off;
     item_coords<V>(s, v, tb, off);
     const int es = s.estride;
     uint32_t *e = sm + tb * (P * es) + off;
-    const uint4 *M = reinterpret_cast<const uint4 *>(tab + (WIDE ? s.tab_off_w : s.tab_off) + item_row(s, tb, off) * (P * RW));
+    const uint4 *M = reinterpret_cast<const uint4 *>(tab + (WIDE ? s.tab_off_w : s.tab_off) + item_row(s, tb, off) * (P * PP));
     uint32_t x[P][V];
     if (CONTIG) {
         if (P % 4 == 0) {
@@ -100,12 +114,12 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
         mx_static_for<P>([&](auto C) { ld_cols<V>(e + decltype(C)::value * es, x[decltype(C)::value]); });
     }
     uint32_t oo[CONTIG ? P : 1];
-    uint32_t xh[WIDE ? P : 1][V];
     if (WIDE) {
+        const uint32_t hq = (q - 1) >> 1;
         mx_static_for<P>([&](auto C) {
             constexpr int c = decltype(C)::value;
 #pragma unroll
-            for (int k = 0; k < V; ++k) { xh[WIDE ? c : 0][k] = x[c][k] >> 16; x[c][k] &= 0xffffu; }
+            for (int k = 0; k < V; ++k) x[c][k] = (uint32_t)mx_centre(x[c][k], q, hq);
         });
     }
     mx_static_for<P>([&](auto R) {
@@ -115,41 +129,36 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
         for (int k = 0; k < V; ++k) acc[k] = acc2[k] = 0;
         mx_static_for<PP / 4>([&](auto K) {
             constexpr int k4 = decltype(K)::value;
-            const uint4 m4 = M[r * (RW / 4) + k4];
+            const uint4 m4 = M[r * (PP / 4) + k4];
             const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
             mx_static_for<4>([&](auto J) {
                 constexpr int c = 4 * k4 + decltype(J)::value;
                 if (c < P) {
 #pragma unroll
                     for (int k = 0; k < V; ++k) {
-                        if (AB_MX_SPLIT && (c & 1)) acc2[k] += (uint64_t)x[c % P][k] * mm[decltype(J)::value];
+                        if (WIDE) {
+                            const int64_t t = (int64_t)(int32_t)x[c % P][k] * (int32_t)mm[decltype(J)::value];
+                            if (NA == 2 && c >= PH) acc2[k] += (uint64_t)t;
+                            else acc[k] += (uint64_t)t;
+                        } else if (AB_MX_SPLIT && (c & 1)) acc2[k] += (uint64_t)x[c % P][k] * mm[decltype(J)::value];
                         else acc[k] += (uint64_t)x[c % P][k] * mm[decltype(J)::value];
                     }
                 }
             });
-            if (WIDE) {
-                const uint4 h4 = M[r * (RW / 4) + PP / 4 + k4];
-                const uint32_t hh[4] = {h4.x, h4.y, h4.z, h4.w};
-                mx_static_for<4>([&](auto J) {
-                    constexpr int c = 4 * k4 + decltype(J)::value;
-                    if (c < P) {
-#pragma unroll
-                        for (int k = 0; k < V; ++k) {
-                            if (AB_MX_SPLIT && (c & 1)) acc2[k] += (uint64_t)xh[WIDE ? c % P : 0][k] * hh[decltype(J)::value];
-                            else acc[k] += (uint64_t)xh[WIDE ? c % P : 0][k] * hh[decltype(J)::value];
-                        }
-                    }
-                });
-            }
         });
         uint32_t o[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            if (AB_MX_SPLIT) acc[k] += acc2[k];
-            const uint32_t mq = (uint32_t)acc[k] * qinv_neg;
-            uint32_t t = (uint32_t)((acc[k] + (uint64_t)mq * q) >> 32);
-            if (!WIDE && P > 4) t = ab_csub(t, 2 * q);
-            o[k] = ab_csub(t, q);
+            if (WIDE) {
+                o[k] = mx_redc_s((int64_t)acc[k], q, qinv_neg);
+                if (NA == 2) o[k] = ab_addmod(o[k], mx_redc_s((int64_t)acc2[k], q, qinv_neg), q);
+            } else {
+                if (AB_MX_SPLIT) acc[k] += acc2[k];
+                const uint32_t mq = (uint32_t)acc[k] * qinv_neg;
+                uint32_t t = (uint32_t)((acc[k] + (uint64_t)mq * q) >> 32);
+                if (P > 4) t = ab_csub(t, 2 * q);
+                o[k] = ab_csub(t, q);
+            }
         }
         if (CONTIG) oo[CONTIG ? r : 0] = o[0];
         else st_cols<V>(e + r * es, o);      // all inputs are already in registers: in place is safe
@@ -175,53 +184,62 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
 // Forward: u_j = x_j + x_(p-j), v_j = x_j - x_(p-j) (x_(p-1) = 0), out_i / out_(p-i) = x_0 + sum_j u_j C_ij +/- sum_j v_j S_ij.
 // Inverse: U_k = X_k + X_(p-k), V_k = X_k - X_(p-k), y_j / y_(p-j) = sum_k U_k C'_jk -/+ sum_k V_k S'_jk, y_0 = sum_k U_k / p,
 // x_j = y_j - y_(p-1).  P = p - 1 inputs and outputs, h = P / 2 products per 64-bit sum, two sums per pair of outputs: half the
-// IMAD.WIDE of the dense step.  The sums u, v stay unreduced (below 2q): narrow T < P q^2 as in the dense step; WIDE splits them
-// into 16-bit halves against the two constant sets (terms below 2^47).
+// IMAD.WIDE of the dense step.  narrow: the sums u, v stay unreduced (below 2q), T < P q^2 as in the dense step; WIDE: u, v reduced
+// and centred, signed sums of h <= 6 products below q^2 / 4.
 template <int H, int V, bool WIDE>
 __device__ __forceinline__ void pair_dot(const uint4 *__restrict__ row, const uint32_t (*xa)[V], const uint32_t (*xb)[V], uint32_t q, uint32_t qinv_neg,
                                          uint32_t (&a)[V], uint32_t (&b)[V]) {
-    // row: [A_1..A_H, B_1..B_H, pad] (and, WIDE, the same times 2^16); xa[j], xb[j] (j < H): the factors of the A and B constants
+    // row: [A_1..A_H, B_1..B_H, pad]; xa[j], xb[j] (j < H): the factors of the A and B constants (WIDE: centred, as int32)
     constexpr int PP = (2 * H + 3) & ~3;
-    uint32_t c[PP], ch[WIDE ? PP : 1];
+    uint64_t sa[V], sb[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) sa[k] = sb[k] = 0;
     mx_static_for<PP / 4>([&](auto K) {
-        constexpr int k = decltype(K)::value;
-        const uint4 t = row[k];
-        c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
-        if (WIDE) {
-            const uint4 u = row[PP / 4 + k];
-            ch[WIDE ? 4 * k : 0] = u.x; ch[WIDE ? 4 * k + 1 : 0] = u.y; ch[WIDE ? 4 * k + 2 : 0] = u.z; ch[WIDE ? 4 * k + 3 : 0] = u.w;
-        }
+        constexpr int k4 = decltype(K)::value;
+        const uint4 t = row[k4];
+        const uint32_t c[4] = {t.x, t.y, t.z, t.w};
+        mx_static_for<4>([&](auto J) {
+            constexpr int idx = 4 * k4 + decltype(J)::value;
+            if (idx < 2 * H) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const uint32_t f = idx < H ? xa[idx % H][k] : xb[idx % H][k];
+                    const uint64_t pr = WIDE ? (uint64_t)((int64_t)(int32_t)f * (int32_t)c[decltype(J)::value]) : (uint64_t)f * c[decltype(J)::value];
+                    if (idx < H) sa[k] += pr;
+                    else sb[k] += pr;
+                }
+            }
+        });
     });
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-        uint64_t sa = 0, sb = 0;
-        mx_static_for<H>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            if (WIDE) {
-                sa += (uint64_t)(xa[j][k] & 0xffffu) * c[j] + (uint64_t)(xa[j][k] >> 16) * ch[WIDE ? j : 0];
-                sb += (uint64_t)(xb[j][k] & 0xffffu) * c[H + j] + (uint64_t)(xb[j][k] >> 16) * ch[WIDE ? H + j : 0];
-            } else {
-                sa += (uint64_t)xa[j][k] * c[j];
-                sb += (uint64_t)xb[j][k] * c[H + j];
-            }
-        });
-        uint32_t ta = (uint32_t)((sa + (uint64_t)((uint32_t)sa * qinv_neg) * q) >> 32);
-        uint32_t tb = (uint32_t)((sb + (uint64_t)((uint32_t)sb * qinv_neg) * q) >> 32);
-        if (!WIDE && H > 2) { ta = ab_csub(ta, 2 * q); tb = ab_csub(tb, 2 * q); }
-        a[k] = ab_csub(ta, q);
-        b[k] = ab_csub(tb, q);
+        if (WIDE) {
+            a[k] = mx_redc_s((int64_t)sa[k], q, qinv_neg);
+            b[k] = mx_redc_s((int64_t)sb[k], q, qinv_neg);
+        } else {
+            uint32_t ta = (uint32_t)((sa[k] + (uint64_t)((uint32_t)sa[k] * qinv_neg) * q) >> 32);
+            uint32_t tb = (uint32_t)((sb[k] + (uint64_t)((uint32_t)sb[k] * qinv_neg) * q) >> 32);
+            if (H > 2) { ta = ab_csub(ta, 2 * q); tb = ab_csub(tb, 2 * q); }
+            a[k] = ab_csub(ta, q);
+            b[k] = ab_csub(tb, q);
+        }
     }
 }
 template <int P, int V, bool WIDE, bool INVS, bool CONTIG = false>
 __device__ __forceinline__ void pair_item(uint32_t *sm, const uint32_t *__restrict__ tab, const AbMxStep &s, int v, uint32_t q, uint32_t qinv_neg) {
     static_assert(P % 2 == 0 && P >= 4, "pair steps are for odd primes p >= 5");
     static_assert(!CONTIG || V == 1, "contiguous items have one column");
-    constexpr int H = P / 2, PP = (P + 3) & ~3, RW = WIDE ? 2 * PP : PP;
+    constexpr int H = P / 2, PP = (P + 3) & ~3, RW = PP;
     int tb, off;
     item_coords<V>(s, v, tb, off);
     const int es = s.estride;
     uint32_t *e = sm + tb * (P * es) + off;
     const uint4 *M = reinterpret_cast<const uint4 *>(tab + (WIDE ? s.tab_off_w : s.tab_off));
+    const uint32_t hq = (q - 1) >> 1;
+    // the sums u = a + b and differences v = a - b that multiply the constants.  narrow: left unreduced (below 2q, T < P q^2);
+    // WIDE: reduced and centred (|.| <= (q-1)/2), as the signed sums need
+    auto usum = [&](uint32_t a, uint32_t b) { return WIDE ? (uint32_t)mx_centre(ab_addmod(a, b, q), q, hq) : a + b; };
+    auto udif = [&](uint32_t a, uint32_t b) { return WIDE ? (uint32_t)mx_centre(ab_submod(a, b, q), q, hq) : a - b + q; };
     uint32_t x[P][V];
     if (CONTIG) {
         if (P % 4 == 0) {
@@ -250,12 +268,12 @@ __device__ __forceinline__ void pair_item(uint32_t *sm, const uint32_t *__restri
         uint32_t xa[H][V], xb[H][V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            xa[0][k] = x[1][k]; xb[0][k] = x[1][k];
+            xa[0][k] = xb[0][k] = WIDE ? (uint32_t)mx_centre(x[1][k], q, hq) : x[1][k];
             mx_static_for<H - 1>([&](auto J) {
                 constexpr int j = decltype(J)::value + 2;
                 const uint32_t a = x[j][k], b = x[(P + 1 - j) % P][k];
-                xa[j - 1][k] = a + b;
-                xb[j - 1][k] = a - b + q;
+                xa[j - 1][k] = usum(a, b);
+                xb[j - 1][k] = udif(a, b);
             });
         }
         mx_static_for<H>([&](auto I) {
@@ -279,8 +297,8 @@ __device__ __forceinline__ void pair_item(uint32_t *sm, const uint32_t *__restri
             mx_static_for<H>([&](auto J) {
                 constexpr int kk = decltype(J)::value + 1;
                 const uint32_t a = x[kk - 1][k], b = x[P - kk][k];
-                xa[kk - 1][k] = a + b;
-                xb[kk - 1][k] = a - b + q;
+                xa[kk - 1][k] = usum(a, b);
+                xb[kk - 1][k] = udif(a, b);
             });
         uint32_t y0[V], dummy[V], c[V];
         pair_dot<H, V, WIDE>(M, xa, xb, q, qinv_neg, y0, dummy);      // row 0: (1/p, ..., 1/p | 0, ..., 0)

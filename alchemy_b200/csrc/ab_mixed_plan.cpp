@@ -20,9 +20,11 @@
 //         x_j = y_j - y_(p-1),   y_j, y_(p-j) = sum_k U_k C'_jk  -/+  sum_k V_k S'_jk,   U_k, V_k = X_k +/- X_(p-k),  C', S' = C, S / p,
 //     and y_0 = (sum_k U_k) / p.  64-bit multiply-accumulate (IMAD.WIDE) is the slowest multiply of the SM -- measured 23 lanes
 //     per clock per SM on B200 against 63 for a 32-bit IMAD (tools/micro/pipes.cu) -- and these steps were most of them.
-// For 2^30 <= q < 2^31 the 64-bit sum of full products would overflow: those limbs get a "wide" table with two
-// constants per entry (M 2^32 and M 2^48 mod q) and the kernel splits x into 16-bit halves, so every term is
-// below 2^47 and one reduction per output still suffices.
+// For 2^30 <= q < 2^31 the 64-bit sum of full unsigned products would overflow: those limbs get a "wide" table whose constants
+// are the CENTRED representatives (|c| <= (q-1)/2, stored as int32) and the kernel centres its inputs too, so every signed
+// product is at most q^2 / 4 < 2^60 in magnitude, up to seven of them fit a signed 64-bit sum, and one signed Montgomery
+// reduction per sum still suffices (one IMAD.WIDE per term, as for the narrow moduli; an earlier version split the inputs into
+// 16-bit halves against two constant sets: two IMAD.WIDE per term).
 #include <algorithm>
 #include <cstring>
 
@@ -58,29 +60,28 @@ uint32_t magic_for(uint32_t d, uint32_t vmax) {
 inline int row_stride(int P) { return (P + 3) & ~3; }   // matrix rows padded to 16 bytes
 
 uint64_t to_mont(uint64_t c, uint64_t q) { return (uint64_t)((((unsigned __int128)c) << 32) % q); }
+// table word of a constant: Montgomery form; wide limbs (mode 2) store the centred representative as a two's complement int32
+uint32_t tab_word(uint64_t c, uint64_t q, int mode) {
+    const uint64_t m = to_mont(c, q);
+    if (mode == 2 && m > (q - 1) / 2) return (uint32_t)(int32_t)((int64_t)m - (int64_t)q);
+    return (uint32_t)m;
+}
 
-// a list of P x P matrices (plain residues) -> Montgomery form, rows padded, appended to limb l's table.
-// narrow: PP words per row (M 2^32 mod q); wide: 2 PP words per row (then M 2^48 mod q)
+// a list of P x P matrices (plain residues) -> Montgomery form (wide limbs: centred), rows padded to 16 bytes, appended to limb l's table
 void push_matrices(Builder &B, int l, const std::vector<std::vector<uint64_t>> &mats, int P, uint64_t q) {
     const int PP = row_stride(P);
     for (auto &M : mats)
-        for (int r = 0; r < P; ++r) {
-            for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < P ? (uint32_t)to_mont(M[r * P + c], q) : 0u);
-            if (B.mode[l] == 2)
-                for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < P ? (uint32_t)((to_mont(M[r * P + c], q) << 16) % q) : 0u);
-        }
+        for (int r = 0; r < P; ++r)
+            for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < P ? tab_word(M[r * P + c], q, B.mode[l]) : 0u);
 }
 
 // tables of a pair step (kind 2) for the prime p with w = omega_p: row i = 1..h holds C_i1..C_ih, S_i1..S_ih (forward) or the same
-// divided by p (inverse, preceded by the row of y_0: h times 1/p, then zeros); Montgomery form, rows padded to 16 bytes; the wide
-// layout appends to every row its copy times 2^16.
+// divided by p (inverse, preceded by the row of y_0: h times 1/p, then zeros); Montgomery form (wide limbs: centred), rows padded to 16 bytes.
 void push_pair_tables(Builder &B, int l, int p, uint64_t w, uint64_t q, bool inverse) {
     const int P = p - 1, h = P / 2, PP = row_stride(P);
     const uint64_t inv2 = invmod(2 % q, q), invp = invmod((uint64_t)p % q, q), winv = invmod(w, q);
     auto emit_row = [&](const std::vector<uint64_t> &row) {
-        for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < (int)row.size() ? (uint32_t)to_mont(row[c], q) : 0u);
-        if (B.mode[l] == 2)
-            for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < (int)row.size() ? (uint32_t)((to_mont(row[c], q) << 16) % q) : 0u);
+        for (int c = 0; c < PP; ++c) B.tab[l].push_back(c < (int)row.size() ? tab_word(row[c], q, B.mode[l]) : 0u);
     };
     if (inverse) {
         std::vector<uint64_t> row(P, 0);
@@ -330,11 +331,11 @@ void ab_build_mixed(ab_plan *pl) {
         if (s.kind == 2) {
             const int words = (s.span / 2 + (inverse ? 1 : 0)) * row_stride(s.span);      // h (+ 1: the y_0 row) rows of 2 h constants
             B.off_n += words;
-            B.off_w += 2 * words;
+            B.off_w += words;
         } else if (s.kind == 0) {
             const int words = s.rows * s.span * row_stride(s.span);
             B.off_n += words;
-            B.off_w += 2 * words;
+            B.off_w += words;
         } else {
             const int words = 2 * (s.rows * (s.span - 1) + 1);
             B.off_n += words;
@@ -378,7 +379,8 @@ void ab_build_mixed(ab_plan *pl) {
         pl->mx_tab_fwd[l] = df;
         pl->mx_tab_inv[l] = di;
         // accumulator bounds of the kernel.  narrow: P (q-1)^2 + (2^32 - 1) q < 2^64 and the reduced value below 4q;
-        // wide: 2 P terms below 2^16 q each, always far below 2^63 for q < 2^31
+        // wide: at most T = ceil(P / 2) (P > 7), P (dense) or P / 2 (pair step) signed products of centred factors per sum:
+        // T ((q-1)/2)^2 < 2^63, and the signed Montgomery result |t| <= T ((q-1)/2)^2 / 2^32 + q / 2 must fit an int32
         const unsigned __int128 q = (unsigned __int128)pl->q[l];
         bool ok = true;
         if (mode[l] == 1)
@@ -386,6 +388,13 @@ void ab_build_mixed(ab_plan *pl) {
                 if (s.kind == 0 || s.kind == 2) {      // kind 2: span / 2 terms with a factor below 2 q each
                     ok = ok && ((unsigned __int128)s.span * (q - 1) * (q - 1) + (((unsigned __int128)1 << 32) - 1) * q < ((unsigned __int128)1 << 64));
                     ok = ok && ((unsigned __int128)s.span * q < ((unsigned __int128)3 << 32));
+                }
+        if (mode[l] == 2)
+            for (auto &s : F.steps)
+                if (s.kind == 0 || s.kind == 2) {
+                    const unsigned __int128 T = s.kind == 2 ? s.span / 2 : (s.span > 7 ? (s.span + 1) / 2 : s.span), hq = (q - 1) / 2;
+                    ok = ok && (T * hq * hq < ((unsigned __int128)1 << 63));
+                    ok = ok && (((T * hq * hq) >> 32) + q / 2 + 2 < ((unsigned __int128)1 << 31));
                 }
         pl->mx_ok[l] = ok ? (uint8_t)mode[l] : 0;
     }

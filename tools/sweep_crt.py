@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--cases", default="pow2,mixed")
     ap.add_argument("--peak", type=float, default=6461.5)
     ap.add_argument("--only", type=int, default=0, help="a single index m with the four 30-bit synthetic moduli")
+    ap.add_argument("--moduli", default="", help="with --only: comma-separated moduli instead of the synthetic ones")
     ap.add_argument("--bytes", type=int, default=1 << 30)
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
@@ -69,7 +70,7 @@ def main():
         cases += [(40320, CFG2[:4]), (11648, TUNNEL_Q[:2]), (29120, TUNNEL_Q[:1]), (43680, RLWR_Q[:5]), (54600, RLWR_Q[:5]),
                   (27300, RLWR_Q[:5]), (20475, RLWR_Q[:4])]
     if args.only:
-        cases = [(args.only, CFG2[:4])]
+        cases = [(args.only, [int(v) for v in args.moduli.split(",")] if args.moduli else CFG2[:4])]
     for m, q in cases:
         r = time_case(m, q, target_bytes=args.bytes, iters=args.iters)
         r["crt_frac"] = r["crt_gbs"] / args.peak
