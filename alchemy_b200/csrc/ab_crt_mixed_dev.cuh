@@ -78,8 +78,8 @@ __device__ __forceinline__ int32_t mx_centre(uint32_t x, uint32_t q, uint32_t hq
 __device__ __forceinline__ uint32_t mx_redc_s(int64_t T, uint32_t q, uint32_t qinv_neg) {
     const int32_t m = (int32_t)((uint32_t)T * (0u - qinv_neg));
     int32_t t = (int32_t)(T >> 32) - __mulhi(m, (int32_t)q);
-    t += (t >> 31) & (int32_t)q;
-    t += (t >> 31) & (int32_t)q;
+    if (t < 0) t += (int32_t)q;
+    if (t < 0) t += (int32_t)q;
     return ab_csub((uint32_t)t, q);
 }
 
@@ -366,9 +366,10 @@ __device__ __forceinline__ void radix2_item(uint32_t *sm, const uint32_t *__rest
                             x[c][k] = a + b;
                             x[d][k] = a - b + 2 * q;
                         } else {
-                            const uint32_t a = x[c][k], b = ab_shoup(x[d][k], w.x, w.y, q);
-                            x[c][k] = ab_addmod(a, b, q);
-                            x[d][k] = ab_submod(a, b, q);
+                            // q >= 2^30: values stay below 2q between the stages of a group (2q < 2^32), one final subtraction
+                            const uint32_t a = t == 0 ? x[c][k] : ab_csub(x[c][k], q), b = ab_shoup(x[d][k], w.x, w.y, q);
+                            x[c][k] = a + b;
+                            x[d][k] = a - b + q;
                         }
                     } else {
                         const uint32_t a = x[c][k], b = x[d][k];
@@ -395,7 +396,7 @@ __device__ __forceinline__ void radix2_item(uint32_t *sm, const uint32_t *__rest
         for (int k = 0; k < V; ++k) {
             uint32_t t = x[c][k];
             if (LAZY && !INV) t = ab_csub(t, 2 * q);
-            if (LAZY) t = ab_csub(t, q);
+            if (LAZY || !INV) t = ab_csub(t, q);
             o[k] = t;
         }
         st_cols<V>(e + c * es, o);

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
             auto term = [&](int) {
                 const uint4 ha = __ldg(reinterpret_cast<const uint4 *>(hb)), hb2 = __ldg(reinterpret_cast<const uint4 *>(hb + 16));
                 uint4 x;
-                if (rep) x = make_uint4(*b0, *b1, *b2, *b3);
+                if (rep && !mac.rep4) x = make_uint4(*b0, *b1, *b2, *b3);
                 else x = *reinterpret_cast<const uint4 *>(b0);
                 hb += hstep; b0 += nb; b1 += nb; b2 += nb; b3 += nb;
                 s00 += (uint64_t)x.x * ha.x; s01 += (uint64_t)x.x * ha.y;

@@ -218,6 +218,9 @@ struct AbMxMac {
     // transform is phi(s') / phi(e') times smaller.  n_out = 0: plain mode (hint, sums and output over the plan's own n).
     const int32_t *rep_idx;
     int32_t n_out, group;        // group: digit transforms held in shared memory per inner-product pass (1..8; filled in by the launcher)
+    int32_t rep4, pad_rep;       // replicated mode: every aligned group of four output rows reads four CONSECUTIVE sub-ring rows starting at a
+                                 // multiple of four (true whenever the innermost axis is shared and a multiple of 4 long): one 16-byte shared load
+                                 // per group instead of four 4-byte loads, which sat four lanes on every bank (3.3 x the ideal wavefronts measured)
     void *acc;                   // scratch of ab_mixed_mac_scratch_words() int64 words (may be null when that is 0)
     int64_t *tbuf;               // optional scratch of [unit][parts][L][n] int64 words (used as uint32: the source residues gathered once per (k, source limb))
     int64_t *out;                // [unit][2][L][n]

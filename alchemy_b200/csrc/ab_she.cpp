@@ -323,6 +323,7 @@ struct ab_tunnel {
     // with CRT tables for e' over the moduli of s', root omega_s'^(s'/e')) and are replicated through es_crt->d_base_crt
     ab_plan *ecrt = nullptr;
     ab_ext *es_crt = nullptr;
+    bool rep4 = false;             // es_crt->d_base_crt maps every aligned group of four rows of O_s' to four consecutive, aligned rows of O_e'
 };
 
 extern "C" int ab_tunnel_create(ab_tunnel **out, const ab_plan *plan_r, const ab_plan *plan_e, const ab_plan *plan_s) {
@@ -368,6 +369,15 @@ extern "C" int ab_tunnel_create(ab_tunnel **out, const ab_plan *plan_r, const ab
                 roots.push_back((int64_t)abh::powmod((uint64_t)plan_s->root[l], (uint64_t)(plan_s->m / plan_e->m), (uint64_t)plan_s->q[l]));
             if (ab_plan_create(&t->ecrt, pe.data(), (int32_t)pe.size(), plan_s->q.data(), plan_s->L, roots.data()) != AB_OK) t->ecrt = nullptr;
             else if (ab_ext_create(&t->es_crt, t->ecrt, plan_s) != AB_OK) { ab_plan_destroy(t->ecrt); t->ecrt = nullptr; t->es_crt = nullptr; }
+            if (t->es_crt && (ns & 3) == 0) {
+                std::vector<int32_t> base(ns);
+                AB_CHECK_CUDA(cudaMemcpy(base.data(), t->es_crt->d_base_crt, ns * 4, cudaMemcpyDeviceToHost));
+                bool ok = true;
+                for (int64_t j = 0; j < ns && ok; j += 4)
+                    ok = (base[j] & 3) == 0 && base[j + 1] == base[j] + 1 && base[j + 2] == base[j] + 2 && base[j + 3] == base[j] + 3;
+                static const bool off = getenv("AB_NO_REP4") && atoi(getenv("AB_NO_REP4")) != 0;      // A/B measurements only
+                t->rep4 = ok && !off;
+            }
         }
         *out = t;
     });
@@ -488,7 +498,7 @@ extern "C" int ab_tunnel_dev(const ab_tunnel *t, int64_t *out2_s, const int64_t 
                 if (sub_ok) {
                     // digits of embed(coeffs_k(c1)) = embed(digits of coeffs_k(c1)): transform them in O_e' and replicate (embedCRT)
                     fx.gather = t->er->d_coeff;
-                    mac.rep_idx = t->es_crt->d_base_crt; mac.n_out = (int32_t)ns;
+                    mac.rep_idx = t->es_crt->d_base_crt; mac.n_out = (int32_t)ns; mac.rep4 = t->rep4 ? 1 : 0;
                     ab_launch_crt_mixed_mac(t->ecrt, B, nlimbs, fx, mac, st);
                 } else {
                     fx.gather = t->d_pow;
