@@ -62,8 +62,10 @@ void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, 
     }
     const size_t smem = ((size_t)max_words + (size_t)p->n) * sizeof(uint32_t);
     AB_REQUIRE(smem <= 227 * 1024, AB_ERR_UNSUPPORTED, "ring too large for the shared-memory transform");
-    // grid.x is limited to 2^31-1, grid.y = limbs
-    const dim3 grid((unsigned)v.batch, (unsigned)v.nlimbs);
+    // one-dimensional grid over (ring element, limb); grid.x is limited to 2^31-1
+    AB_REQUIRE(v.batch * v.nlimbs < (1ll << 31), AB_ERR_ARG, "batch too large for one launch");
+    args.interleave = ab_mx_interleave();
+    const dim3 grid((unsigned)(v.batch * v.nlimbs));
     static const int force_t = getenv("AB_MX_T") ? atoi(getenv("AB_MX_T")) : 0;      // experiments only
     const int T = force_t ? force_t : pick_threads(steps, (int)p->n, smem);
     if (inverse) ab_mx_launch_inv(grid, T, smem, st, args, v.y);

@@ -18,6 +18,7 @@ struct MxArgs {
         int32_t wide, pad;         // table layout of this limb (ab_mixed_plan.cpp)
     } limb[AB_MAX_LIMBS];
     int32_t nsteps, n, nlimbs;
+    int32_t interleave, pad_il;    // grid order: 0 = limb-major (default), 1 = limbs interleaved (AB_MX_INTERLEAVE=1)
     int32_t tab_words[2];          // narrow, wide
     int64_t batch;
     int64_t estride, lstride, bstride;   // int64 strides of coefficient, limb, ring element
@@ -691,6 +692,13 @@ static inline int pick_threads(const std::vector<AbMxStep> &steps, int n, size_t
     return best_t;
 }
 
+static inline int ab_mx_interleave() {
+    // A/B measurements only.  Measured on B200: HomomRLWR mul_ level 1 +3 %, the CRT sweep unchanged except m = 27300 (five limbs,
+    // n = 5760) -12 %: left off
+    static const int v = (getenv("AB_MX_INTERLEAVE") && atoi(getenv("AB_MX_INTERLEAVE"))) ? 1 : 0;
+    return v;
+}
+
 static inline uint32_t neg_inv32(uint32_t q) {   // -q^-1 mod 2^32 (Newton)
     uint32_t x = q;                        // q odd: x = q is an inverse mod 8
     for (int i = 0; i < 5; ++i) x *= 2u - q * x;
@@ -705,6 +713,7 @@ static inline void fill_mx_args(const ab_plan *p, MxArgs &args, int32_t limb0, i
     args.tab_words[0] = inverse ? p->mx_words_inv[0] : p->mx_words_fwd[0];
     args.tab_words[1] = inverse ? p->mx_words_inv[1] : p->mx_words_fwd[1];
     args.nlimbs = nlimbs;
+    args.interleave = ab_mx_interleave();
     max_words = 0;
     for (int l = 0; l < nlimbs; ++l) {
         const AbLimbDev &ld = p->limb[limb0 + l];

@@ -6,14 +6,17 @@
 template <bool INV>
 __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_constant__ MxArgs args, int64_t *__restrict__ y) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int limb = blockIdx.y;
+    // one-dimensional grid over (ring element, limb), limb-major; AB_MX_INTERLEAVE=1 interleaves the limbs (block b = ring element
+    // b / L, limb b % L) so that the ALU-heavy transforms of the moduli above 2^30 sit beside the IMAD-heavy ones of the narrow moduli
+    const int limb = args.interleave ? (int)(blockIdx.x % (unsigned)args.nlimbs) : (int)(blockIdx.x / (unsigned)args.batch);
+    const unsigned bx = args.interleave ? blockIdx.x / (unsigned)args.nlimbs : blockIdx.x % (unsigned)args.batch;
     const bool wide = args.limb[limb].wide != 0;
     const int tab_words = args.tab_words[wide ? 1 : 0];
     uint32_t *tab = smem;                          // [tab_words]
     uint32_t *sm = smem + tab_words;               // [n]
     const uint32_t q = args.limb[limb].q, qinv_neg = args.limb[limb].qinv_neg;
     const int n = args.n;
-    int64_t *yp = y + blockIdx.x * args.bstride + limb * args.lstride;
+    int64_t *yp = y + bx * args.bstride + limb * args.lstride;
     {   // constant tables of this limb (L2-resident, a few KB)
         const uint4 *src = reinterpret_cast<const uint4 *>(args.limb[limb].tab);
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
@@ -24,8 +27,8 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
         // the residues of this transform are gadget digit d of a powerful-basis element (optionally gathered
         // through an index table: coeffs . embed of the tunnel), centred and reduced into this CTA's modulus
         const AbMxFused &fx = args.fx;
-        const int d = (int)(blockIdx.x % fx.nd);
-        const int64_t unit = blockIdx.x / fx.nd;
+        const int d = (int)(bx % fx.nd);
+        const int64_t unit = bx / fx.nd;
         if (mx_digit_is_trivial(fx, d, limb)) {
             // TrivGad digit of limb l reduced mod q_l is the element itself: its CRT is the caller's CRT-basis input
             const int4 *src = reinterpret_cast<const int4 *>(fx.triv_src + unit * fx.triv_ustride + (int64_t)limb * n);
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
     } else if (args.fx.load_mode == AB_MX_LOAD_GARNER) {
         const AbMxFused &fx = args.fx;
         const int k = fx.gar_k;
-        const int64_t *src = fx.src + blockIdx.x * fx.src_ustride;
+        const int64_t *src = fx.src + bx * fx.src_ustride;
         uint32_t qmod[AB_MX_MAX_DROP];                 // q_i mod q of this CTA
 #pragma unroll
         for (int i = 0; i < AB_MX_MAX_DROP; ++i) qmod[i] = i < k ? fx.gar_q[i] % q : 0u;
@@ -64,8 +67,8 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
         }
     } else if (args.fx.load_mode == AB_MX_LOAD_GATHER) {
         const AbMxFused &fx = args.fx;
-        const int64_t su = blockIdx.x / fx.gK;
-        const int32_t *__restrict__ gt = fx.gather + (int64_t)(blockIdx.x % fx.gK) * n;
+        const int64_t su = bx / fx.gK;
+        const int32_t *__restrict__ gt = fx.gather + (int64_t)(bx % fx.gK) * n;
         const int64_t *__restrict__ src = fx.src + su * fx.src_ustride + (int64_t)limb * fx.n_src;
         for (int j0 = threadIdx.x; j0 < n; j0 += 4 * blockDim.x) {
             int32_t g[4];
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
         }
     } else if (args.fx.load_mode == AB_MX_LOAD_SRC) {
         // out of place: read the transform from another planar buffer (e.g. c2 of a degree-2 ciphertext)
-        const int4 *src = reinterpret_cast<const int4 *>(args.fx.src + blockIdx.x * args.fx.src_ustride + (int64_t)(args.fx.src_limb0 + limb) * n);
+        const int4 *src = reinterpret_cast<const int4 *>(args.fx.src + bx * args.fx.src_ustride + (int64_t)(args.fx.src_limb0 + limb) * n);
         uint2 *dst = reinterpret_cast<uint2 *>(sm);
         for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
             const int4 v = __ldcs(src + i);
@@ -97,14 +100,14 @@ __global__ void __launch_bounds__(256, AB_MX_MINB) k_crt_mixed(const __grid_cons
     }
     (void)skip_program;
     __syncthreads();
-    const bool l_on = args.fx.l_period <= 1 || ((args.fx.l_mask >> ((blockIdx.x + args.fx.l_phase) % args.fx.l_period)) & 1) != 0;
+    const bool l_on = args.fx.l_period <= 1 || ((args.fx.l_mask >> ((bx + args.fx.l_phase) % args.fx.l_period)) & 1) != 0;
     if (!INV && args.fx.pre_l && l_on) mx_l_pass(sm, n, args.fx, q, false);
     if (wide) run_program<INV, true>(args, sm, tab, q, qinv_neg);
     else run_program<INV, false>(args, sm, tab, q, qinv_neg);
     if (INV && args.fx.post_linv && l_on) mx_l_pass(sm, n, args.fx, q, true);
     if (args.fx.store_mode == AB_MX_STORE_SUBSCALE) {
         // RNS rescale epilogue: out = (in - x) * q_drop^-1 mod q   (x = CRT of the lifted dropped limb)
-        const int64_t *in = args.fx.sub_in + blockIdx.x * args.fx.sub_ustride + (int64_t)limb * n;
+        const int64_t *in = args.fx.sub_in + bx * args.fx.sub_ustride + (int64_t)limb * n;
         const uint32_t sc = args.fx.scale[limb], scs = args.fx.scale_s[limb];
         const int4 *src = reinterpret_cast<const int4 *>(in);
         int4 *dst = reinterpret_cast<int4 *>(yp);

@@ -63,7 +63,7 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     args.fx = fx;
     int max_words = 0;
     fill_mx_args(p, args, 0, nlimbs, false, max_words);
-    args.batch = units;
+    args.batch = units * (mac.parts > 1 ? mac.parts : 1);      // CTAs per limb
     args.estride = 1; args.lstride = p->n; args.bstride = p->n * nlimbs;
     AbMxMac mac2 = mac;
     static const bool no_bits = getenv("AB_NO_BITS") && atoi(getenv("AB_NO_BITS")) != 0;      // A/B measurements only
@@ -83,7 +83,8 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     const size_t smem = mac_smem(p, max_words, acc_smem) + (size_t)(group - 1) * nbw;
     static const int force_t = getenv("AB_MX_MAC_T") ? atoi(getenv("AB_MX_MAC_T")) : 0;      // experiments only
     const int T = force_t ? force_t : pick_threads(p->mx_fwd, (int)p->n, smem);
-    const dim3 grid((unsigned)(units * parts), (unsigned)nlimbs);
+    AB_REQUIRE(units * parts * nlimbs < (1ll << 31), AB_ERR_ARG, "batch too large for one launch");
+    const dim3 grid((unsigned)(units * parts * nlimbs));
     if (acc_smem) ab_mx_launch_mac_smem(grid, T, smem, st, args, mac2);
     else ab_mx_launch_mac_glob(grid, T, smem, st, args, mac2);
     ab_count_launch();
@@ -91,6 +92,7 @@ void ab_launch_crt_mixed_mac(const ab_plan *p, int64_t units, int32_t nlimbs, co
     if (parts > 1) {
         const int64_t work = units * nlimbs * (mac.n_out > 0 ? mac.n_out : p->n);
         const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)p->sm_count * 16));
+        args.batch = units;      // the combine pass walks over units, not CTAs
         k_mac_combine<<<g, 256, 0, st>>>(args, mac2);
         ab_count_launch();
         ab_check_launch("mac_combine");

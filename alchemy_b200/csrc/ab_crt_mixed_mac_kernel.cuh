@@ -16,7 +16,8 @@
 template <int MAXT, int MINB, bool ACC_SMEM>
 __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_constant__ MxArgs args, const __grid_constant__ AbMxMac mac) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int limb = blockIdx.y;
+    const int limb = args.interleave ? (int)(blockIdx.x % (unsigned)args.nlimbs) : (int)(blockIdx.x / (unsigned)args.batch);      // as in k_crt_mixed
+    const unsigned bx = args.interleave ? blockIdx.x / (unsigned)args.nlimbs : blockIdx.x % (unsigned)args.batch;
     const bool wide = args.limb[limb].wide != 0;
     const int tab_words = args.tab_words[wide ? 1 : 0];
     const int n = args.n, nb = (n + 3) & ~3;
@@ -25,8 +26,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
     const uint32_t q = args.limb[limb].q, qinv_neg = args.limb[limb].qinv_neg;
     const AbMxFused &fx = args.fx;
     const int parts = mac.parts > 1 ? mac.parts : 1;
-    const int64_t unit = blockIdx.x / parts, slice = blockIdx.x;          // slice = unit * parts + part
-    const int part = (int)(blockIdx.x - unit * parts);
+    const int64_t unit = bx / parts, slice = bx;          // slice = unit * parts + part
+    const int part = (int)(bx - unit * parts);
     const int nm = (!ACC_SMEM && mac.n_out > 0) ? mac.n_out : n;       // positions of the inner product (hint, sums, output)
     const int32_t *rep = (!ACC_SMEM && mac.n_out > 0) ? mac.rep_idx : nullptr;
     uint2 *acc = ACC_SMEM ? reinterpret_cast<uint2 *>(sm + nb)

@@ -62,7 +62,9 @@ def workload(args):
 
 def measured_traffic(m, L, batch):
     """DRAM bytes per launch of the two CRT kernels from the committed ncu capture (profiles/), if it is for this workload"""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
@@ -199,6 +201,46 @@ def mul_keyswitch_leg(ab, torch, iters=5):
     return out
 
 
+# ------------------------------------------------------------------------------------------ config 3
+def mixed_leg(ab, torch, peak, iters=10):
+    """BASELINE config 3: batched CRT / crtInv on the non-power-of-two index m = 40320 = 2^7 3^2 5 7 (n = 9216, mixed-radix stages),
+    same four moduli, ~1 GiB in place (larger than L2), CUDA events per direction on the launching stream."""
+    m, moduli = 40320, CFG2_MODULI
+    plan = ab.Plan(m, moduli)
+    n, L = plan.n, len(moduli)
+    batch = (1 << 30) // (8 * n * L)
+    y = torch.empty((batch, L, n), dtype=torch.int64, device="cuda")
+    for l, q in enumerate(moduli):
+        y[:, l] = torch.randint(0, q, (batch, n), dtype=torch.int64, device="cuda")
+    head = y[:2].clone()
+    st = torch.cuda.current_stream()
+    sp, yp, lib = C.c_void_p(st.cuda_stream), C.c_void_p(y.data_ptr()), ab.lib()
+    out = {"workload": f"batched CRT / crtInv, m={m} (n={n}), L={L}, B={batch}", "kernel": "k_crt_mixed<0> / k_crt_mixed<1>", "bytes_per_launch": 16 * n * batch * L}
+    for name, fn in (("fwd", lib.ab_crt_dev), ("inv", lib.ab_crt_inv_dev)):
+        for _ in range(3):
+            ab.check(lib.ab_crt_dev(plan.h, yp, batch, 0, L, ab.PLANAR, sp))
+            ab.check(lib.ab_crt_inv_dev(plan.h, yp, batch, 0, L, ab.PLANAR, sp))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(st)
+        for _ in range(iters):
+            ab.check(fn(plan.h, yp, batch, 0, L, ab.PLANAR, sp))
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[name + "_ms"] = ms
+        out[name + "_gbs"] = out["bytes_per_launch"] / (ms * 1e-3) / 1e9
+        out[name + "_frac"] = out[name + "_gbs"] / peak
+        # undo the `iters` one-directional applications so that the round-trip check below sees the input
+        for _ in range(iters):
+            ab.check((lib.ab_crt_inv_dev if name == "fwd" else lib.ab_crt_dev)(plan.h, yp, batch, 0, L, ab.PLANAR, sp))
+    torch.cuda.synchronize()
+    assert torch.equal(head, y[:2]), "mixed-radix crtInv . crt != id"
+    out["transforms_per_s"] = 2 * batch * L / ((out["fwd_ms"] + out["inv_ms"]) * 1e-3)
+    out["frac"] = (out["fwd_frac"] + out["inv_frac"]) / 2
+    return out
+
+
 # ------------------------------------------------------------------------------------------ GPU legs
 def main():
     args = parse()
@@ -308,8 +350,9 @@ def main():
                "api": "ab_tensor_op_host(CRT) + ab_tensor_op_host(CRT_INV), pinned host buffers"}
 
     # ---- secondary metric M2 (rank 0, N = 1 only): ciphertext mul + key-switch pipelines per second
-    m2 = m3 = None
+    m2 = m3 = mx = None
     if rank == 0 and world == 1 and not args.no_m2:
+        mx = mixed_leg(ab, torch, peaks()[0])
         m2 = mul_keyswitch_leg(ab, torch)
         # M3: the ring-tunnelling chain of examples/Tunnel.hs on a slice of the 4096-ciphertext workload (tools/bench_she.py)
         sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -338,6 +381,8 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks}
         if e2e:
             line["e2e"] = e2e
+        if mx:
+            line["crt_mixed"] = mx
         if m2:
             line["mul_keyswitch"] = m2
         if m3:
