@@ -29,7 +29,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant: build a copy with extra -D flags into build_variants/<variant>/ (kernel A/B experiments; load it with
+    ALCHEMY_B200_LIB=<path>); the in-tree library is built without arguments"""
+    global LIBDIR, LIB
+    if variant:
+        LIBDIR = os.path.join(os.path.dirname(HERE), "build_variants", variant)
+        LIB = os.path.join(LIBDIR, "libalchemy_b200.so")
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
@@ -41,7 +47,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -56,4 +62,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(force="--force" in sys.argv, verbose=True, variant=var[0] if var else None, defines=[a[2:] for a in sys.argv if a.startswith("-D")]))

@@ -1,5 +1,6 @@
 // ab_abi.cpp -- extern "C" entry points for the Tensor methods (include/alchemy_b200.h).
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -191,13 +192,15 @@ struct DevBuf {
     DevBuf(const DevBuf &) = delete;
 };
 
-// Host-buffer calls are pipelined: the batch is cut into chunks of about 32 MB that rotate over three
+// Host-buffer calls are pipelined: the batch is cut into chunks of about 16 MB (AB_HOST_CHUNK_MB; measured at n = 32768, L = 4 with
+// four streams: 2 MB 114 k, 4 MB 126 k, 8 MB 150 k, 16 MB 162 k, 32 MB 145 k transforms/s end to end, i.e. 42.5 GB/s per direction of
+// the 49.6 GB/s the box reaches with both directions busy, tools/micro/pcie.py) that rotate over four
 // internal streams (H2D copy, kernels, D2H copy of one chunk are stream-ordered; chunks on different streams
 // overlap), so the two PCIe directions and the kernels run concurrently.  With pinned host memory the copies
 // are truly asynchronous; with pageable memory the runtime stages them and the call still returns the same data.
 struct HostPipe {
-    static constexpr int kStreams = 3;
-    cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
+    static constexpr int kStreams = 4;
+    cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr, nullptr};
     int device = -1;
     void ensure() {
         int dev = 0;
@@ -219,7 +222,8 @@ extern "C" int ab_tensor_op_host(const ab_plan *p, int op, int64_t *y_host, int6
         if (batch == 0) return;
         g_pipe.ensure();
         const size_t item = (size_t)p->L * p->n * sizeof(int64_t);
-        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)((32u << 20) / item)));
+        static const size_t chunk_mb = getenv("AB_HOST_CHUNK_MB") && atoi(getenv("AB_HOST_CHUNK_MB")) > 0 ? (size_t)atoi(getenv("AB_HOST_CHUNK_MB")) : 16;      // experiments
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)((chunk_mb << 20) / item)));
         const bool relayout = layout == AB_LAYOUT_INTERLEAVED && p->L > 1;
         const int ns = (int)std::min<int64_t>(HostPipe::kStreams, (batch + chunk - 1) / chunk);
         std::vector<std::unique_ptr<DevBuf>> d(ns), t(ns);

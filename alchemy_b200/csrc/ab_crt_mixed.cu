@@ -67,7 +67,7 @@ void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, 
     args.interleave = ab_mx_interleave();
     const dim3 grid((unsigned)(v.batch * v.nlimbs));
     static const int force_t = getenv("AB_MX_T") ? atoi(getenv("AB_MX_T")) : 0;      // experiments only
-    const int T = force_t ? force_t : pick_threads(steps, (int)p->n, smem);
+    const int T = force_t ? force_t : pick_threads(steps, (int)p->n, smem, 256 * AB_MX_MINB);
     if (inverse) ab_mx_launch_inv(grid, T, smem, st, args, v.y);
     else ab_mx_launch_fwd(grid, T, smem, st, args, v.y);
     ab_count_launch();

@@ -26,7 +26,14 @@ struct MxArgs {
 };
 
 #ifndef AB_MX_MINB
-#define AB_MX_MINB 4          // resident CTAs per SM the register budget is tuned for
+#define AB_MX_MINB 5          // resident 256-thread CTAs per SM the register budget of the transform kernels is tuned for (48 registers;
+                              // measured against 4 / 64 registers: +1 ... +5 % on the example rings, inverse transforms most)
+#endif
+#ifndef AB_MX_MAC_MINB
+#define AB_MX_MAC_MINB 4      // the fused inner product keeps 64 registers (an 80-register build measured slower, fewer registers spill)
+#endif
+#ifndef AB_MX_REDC_HI
+#define AB_MX_REDC_HI 0       // 1: Montgomery step as hi + umulhi(m, q) + (lo != 0) (an IMAD.HI and two ALU ops) instead of a 64-bit IMAD.WIDE
 #endif
 #ifndef AB_MX_SPLIT
 #define AB_MX_SPLIT 0         // 1: two partial accumulators per output (shorter dependent chain); measured: no gain on B200
@@ -72,6 +79,15 @@ __device__ __forceinline__ void st_cols(uint32_t *p, const uint32_t (&x)[V]) {
 // are moved with 16- or 8-byte shared-memory accesses.  With 4-byte accesses the lanes of a warp sit P words apart and,
 // for P = 12, four of them share every bank (measured: 70 % of all excess shared-memory wavefronts of the transform);
 // lanes reading 16 bytes at a 48-byte pitch cover the 32 banks exactly once per quarter warp.
+// (T + m q) / 2^32 for T < 2^64 - 2^32 q, m = lo(T) * (-q^-1): the low words cancel to 0 mod 2^32 and carry out exactly when lo(T) != 0
+__device__ __forceinline__ uint32_t mx_redc_u(uint64_t T, uint32_t q, uint32_t qinv_neg) {
+    const uint32_t lo = (uint32_t)T, mq = lo * qinv_neg;
+#if AB_MX_REDC_HI
+    return (uint32_t)(T >> 32) + __umulhi(mq, q) + (lo != 0u ? 1u : 0u);
+#else
+    return (uint32_t)((T + (uint64_t)mq * q) >> 32);
+#endif
+}
 // signed helpers of the WIDE path (2^30 <= q < 2^31): centred inputs and constants, signed 64-bit sums
 __device__ __forceinline__ int32_t mx_centre(uint32_t x, uint32_t q, uint32_t hq) { return (int32_t)(x > hq ? x - q : x); }      // [0,q) -> [-hq, hq]
 // signed Montgomery: T 2^-32 mod q for |T| < 2^63, result in [0,q).  qinv = q^-1 mod 2^32 = -qinv_neg.  The low words of T and m q
@@ -155,8 +171,7 @@ __device__ __forceinline__ void matvec_item(uint32_t *sm, const uint32_t *__rest
                 if (NA == 2) o[k] = ab_addmod(o[k], mx_redc_s((int64_t)acc2[k], q, qinv_neg), q);
             } else {
                 if (AB_MX_SPLIT) acc[k] += acc2[k];
-                const uint32_t mq = (uint32_t)acc[k] * qinv_neg;
-                uint32_t t = (uint32_t)((acc[k] + (uint64_t)mq * q) >> 32);
+                uint32_t t = mx_redc_u(acc[k], q, qinv_neg);
                 if (P > 4) t = ab_csub(t, 2 * q);
                 o[k] = ab_csub(t, q);
             }
@@ -218,8 +233,7 @@ __device__ __forceinline__ void pair_dot(const uint4 *__restrict__ row, const ui
             a[k] = mx_redc_s((int64_t)sa[k], q, qinv_neg);
             b[k] = mx_redc_s((int64_t)sb[k], q, qinv_neg);
         } else {
-            uint32_t ta = (uint32_t)((sa[k] + (uint64_t)((uint32_t)sa[k] * qinv_neg) * q) >> 32);
-            uint32_t tb = (uint32_t)((sb[k] + (uint64_t)((uint32_t)sb[k] * qinv_neg) * q) >> 32);
+            uint32_t ta = mx_redc_u(sa[k], q, qinv_neg), tb = mx_redc_u(sb[k], q, qinv_neg);
             if (H > 2) { ta = ab_csub(ta, 2 * q); tb = ab_csub(tb, 2 * q); }
             a[k] = ab_csub(ta, q);
             b[k] = ab_csub(tb, q);
@@ -673,11 +687,11 @@ __device__ __forceinline__ void mx_l_pass(uint32_t *sm, int n, const AbMxFused &
 // 384 items -> 1.5 rounds at T = 256).  Model: time of one transform ~ sum over passes of rounds * work per item,
 // throughput ~ resident CTAs / time; resident CTAs from shared memory and the 64-register budget (1024 threads).
 // Measured on B200 (tools/sweep_crt.py, AB_MX_T): within 3 % of the best of {128, 160, 192, 224, 256} on every example ring.
-static inline int pick_threads(const std::vector<AbMxStep> &steps, int n, size_t smem) {
+static inline int pick_threads(const std::vector<AbMxStep> &steps, int n, size_t smem, int max_threads = 1024) {
     int best_t = 256;
     double best = 0;
     for (int T : {128, 160, 192, 256}) {
-        const int ctas = (int)std::min<size_t>((size_t)(1024 / T), (size_t)(227 * 1024) / (smem + 1024));
+        const int ctas = (int)std::min<size_t>((size_t)(max_threads / T), (size_t)(227 * 1024) / (smem + 1024));
         if (ctas < 1) continue;
         double time = 6.0 * ((n / 2 + T - 1) / T);                 // load + store phases
         for (const AbMxStep &s : steps) {

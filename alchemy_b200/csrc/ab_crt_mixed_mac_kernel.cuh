@@ -187,8 +187,8 @@ void ab_mx_launch_mac_glob(dim3 grid, int T, size_t smem, cudaStream_t st, const
 #endif
     static thread_local bool ready = false;
     if (!ready) {
-        AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_mixed_mac<256, AB_MX_MINB, AB_MX_MAC_SMEM != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_mixed_mac<256, AB_MX_MAC_MINB, AB_MX_MAC_SMEM != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ready = true;
     }
-    k_crt_mixed_mac<256, AB_MX_MINB, AB_MX_MAC_SMEM != 0><<<grid, T, smem, st>>>(args, mac);
+    k_crt_mixed_mac<256, AB_MX_MAC_MINB, AB_MX_MAC_SMEM != 0><<<grid, T, smem, st>>>(args, mac);
 }
