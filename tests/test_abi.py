@@ -23,6 +23,18 @@ def test_header_and_binding_agree():
     assert sorted(_lib.SIGNATURES) == names
 
 
+def test_generated_haskell_binding_matches_the_abi():
+    """haskell/.../B200/FFI.hs (the `foreign import`s a maintainer of the reference would add) is generated from the ABI table and
+    committed: it must be exactly what the generator prints, and name every entry of the header"""
+    import subprocess
+    import sys
+    gen = os.path.join(ROOT, "tools", "gen_haskell_ffi.py")
+    assert subprocess.run([sys.executable, gen, "--check"]).returncode == 0, "run tools/gen_haskell_ffi.py"
+    hs = open(os.path.join(ROOT, "haskell", "Crypto", "Lol", "Cyclotomic", "Tensor", "B200", "FFI.hs")).read()
+    for name in header_functions():
+        assert f'ccall unsafe "{name}"' in hs, name
+
+
 def test_library_exports_every_declared_symbol():
     from alchemy_b200 import _lib
     assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
