@@ -22,7 +22,9 @@ POW2 = [(64, [193, 257]), (128, ARITH_Q[:1]), (256, ARITH_Q), (512, ARITH_Q), (1
 MIXED = [(9, [19, 37]), (27, [109]), (25, [101]), (45, [181, 541]), (36, [37, 73]), (12, [13]), (105, [211, 421]),
          (63, [127]), (40, [41]), (7, [29]), (13, [53]), (72, [73]), (200, [401]), (1, [17]), (2, [17]), (4, [17]),
          (40320, CFG2_Q[:2]), (11648, TUNNEL_Q[:2]), (29120, TUNNEL_Q[:1]), (43680, RLWR_Q[:2]), (54600, RLWR_Q[3:5]),
-         (27300, RLWR_Q[:1]), (20475, RLWR_Q[:3])]
+         (27300, RLWR_Q[:1]), (20475, RLWR_Q[:3]),
+         # the 10-point pair step (p = 11), alone, beside 13 (stride 12: two columns per item) and over a modulus above 2^30 (signed sums)
+         (11, [23, 67]), (55, [331]), (143, [859]), (1001, [1500018521, 2003])]
 # 2^30 < q < 2^31: the exact (non-lazy) butterfly path; 2147483647 = 2^31 - 1
 BIGQ = [(512, 2147483137), (2048, 2013265921), (63, 2147483647), (20475, 2147418001)]
 
@@ -92,6 +94,28 @@ def test_crt_large_moduli_take_the_exact_butterflies():
         assert (y.cpu().numpy() == oracle_limbs(O.crt, m, [q], x)).all()
         ab.GT.crtInv(plan, y)
         assert (y.cpu().numpy() == x).all()
+
+
+@pytest.mark.parametrize("m,moduli", [(20475, RLWR_Q[:1] + RLWR_Q[4:6]), (43680, RLWR_Q[:2]), (40320, CFG2_Q[:1]), (1001, [1500018521, 2003])])
+def test_mixed_kernels_at_the_extremes_of_the_residue_range(m, moduli):
+    """worst cases of the 64-bit sums of the dense and pair steps: all residues q - 1 (narrow: largest unsigned products), all at
+    +-(q-1)/2 and alternating around the centring threshold (wide moduli: largest signed products of either sign, sign handling of the
+    reduced values), against the oracle, forward and inverse"""
+    ab = backend()
+    plan = ab.Plan(m, moduli)
+    n = plan.n
+    rows = []
+    for q in moduli:
+        hq = (q - 1) // 2
+        alt = np.where(np.arange(n) % 2 == 0, hq, hq + 1)
+        rows.append(np.stack([np.full(n, q - 1), np.full(n, hq), np.full(n, hq + 1), alt, (alt[::-1]).copy(), np.where(np.arange(n) % 3 == 0, q - 1, 1)]))
+    x = np.stack(rows, axis=1).astype(np.int64)          # [6, L, n]
+    y = dev(x)
+    ab.GT.crt(plan, y)
+    assert (y.cpu().numpy() == oracle_limbs(O.crt, m, moduli, x)).all()
+    z = dev(x)
+    ab.GT.crtInv(plan, z)
+    assert (z.cpu().numpy() == oracle_limbs(O.crt_inv, m, moduli, x)).all()
 
 
 def test_limb_subrange_and_empty_batch():
