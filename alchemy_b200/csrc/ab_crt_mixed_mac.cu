@@ -48,6 +48,14 @@ int32_t ab_mixed_mac_parts(const ab_plan *p, int64_t units, int32_t nlimbs, int3
     const int64_t slots = (int64_t)p->sm_count * 5, want = 4 * slots;
     int64_t parts = (want + units * nlimbs - 1) / (units * nlimbs);
     parts = std::min<int64_t>(parts, total_digits / 8);
+    // latency regime (round 2): a handful of ciphertexts -- the reference's own timed run is ONE evaluation (examples/HomomRLWR.hs:68) -- does
+    // not even fill one wave with eight digits per CTA: go down to two digits per CTA as long as the grid stays within one wave
+    // (measured on the Tunnel.hs chain, one ciphertext: see profiles/r02_small_batch_latency.jsonl)
+    static const bool no_lat = getenv("AB_MX_MAC_NOLATENCY") && atoi(getenv("AB_MX_MAC_NOLATENCY")) != 0;      // A/B measurements only
+    if (!no_lat && units * nlimbs * std::max<int64_t>(1, parts) < slots) {
+        const int64_t fit = slots / (units * nlimbs);
+        parts = std::max<int64_t>(parts, std::min<int64_t>(fit, total_digits / 2));
+    }
     return (int32_t)std::max<int64_t>(1, parts);
 }
 int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs) {

@@ -247,3 +247,42 @@ def test_every_kernel_variant_computes_the_same_bits(switch):
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_she.py"), "-x", "-q", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_chains_replay_from_a_cuda_graph():
+    """every *_dev entry is asynchronous on the caller's stream with caller-owned scratch, so a chain of them can be captured once
+    into a CUDA graph and replayed (small batches are launch-bound: examples/Tunnel.hs on one ciphertext is 20 launches): a tunnelling
+    hop followed by a rescale, and the one-call `mul_` pipeline, replayed on new inputs, give the bits of the eager calls"""
+    import torch
+
+    import alchemy_b200 as ab
+    from alchemy_b200 import she
+    rng = np.random.default_rng(77)
+    r, e, s_idx, moduli, L, base = 11648, 5824, 29120, TUNNEL_Q, 2, 2
+    pr, pe, ps = ab.Plan(r, moduli), ab.Plan(e, moduli, crt=False), ab.Plan(s_idx, moduli)
+    tn = she.Tunnel(pr, pe, ps)
+    K, D, B = pr.n // pe.n, S.gadget_len(moduli[:L], base), 2
+    flin, hint = dev(rand(rng, (K,), moduli[:L], ps.n)), dev(rand(rng, (K, D, 2), moduli[:L], ps.n))
+    p5 = ab.Plan(20475, RLWR_Q)
+    kh = dev(rand(rng, (3, 2), RLWR_Q[:3], p5.n))
+    pre = [pow(2, -1, q) for q in RLWR_Q[:2]]
+
+    def chain(c, a, b):
+        return she.modSwitch(ps, tn(c, flin, hint, base), 1, 1), she.mulKeySwitch(p5, a, b, kh, 3, 1, 0, prescale=pre, dec_mask=1)
+
+    def inputs():
+        return dev(rand(rng, (B, 2), moduli[:L], pr.n)), dev(rand(rng, (B, 2), RLWR_Q[:2], p5.n)), dev(rand(rng, (B, 2), RLWR_Q[:2], p5.n))
+
+    c, a, b = inputs()
+    chain(c, a, b)                                   # warm-up outside the capture (lazy kernel attributes, allocator)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = chain(c, a, b)
+    for _ in range(2):
+        c2, a2, b2 = inputs()
+        c.copy_(c2); a.copy_(a2); b.copy_(b2)
+        g.replay()
+        torch.cuda.synchronize()
+        want = chain(c2, a2, b2)
+        assert torch.equal(out[0], want[0]) and torch.equal(out[1], want[1])

@@ -100,7 +100,7 @@ def tunnel_chain(total, iters, rank, world):
             "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / PEAK, "launches_per_call": int((ab.lib().ab_kernel_launches() - l0) // (iters + 2))}
 
 
-def rlwr_chain(B, iters):
+def rlwr_chain(B, iters, graph=False):
     """examples/HomomRLWR.hs as a chain of device calls on synthetic ciphertexts and hints: mulPublic,
     five ring-tunnelling hops H0' -> ... -> H5' (TrivGad; modSwitch to the hint modulus, tunnel, modSwitch back: 5 -> 6 -> 5 limbs,
     last hop 5 -> 5 -> 4), then the rescaling tree at H5': 8 `mul_` pipelines (1 + 4 + 2 + 1 over the four levels), 15 div2
@@ -148,8 +148,19 @@ def rlwr_chain(B, iters):
         return cur
     l0 = lib.ab_kernel_launches()
     ms = timeit(run, iters)
-    return {"case": "HomomRLWR.hs evaluation chain (mulPublic, 5 tunnel hops, 8 mul_ pipelines, TrivGad)", "B": B, "ms": ms,
-            "evaluations_per_s": B / (ms * 1e-3), "launches_per_call": int((lib.ab_kernel_launches() - l0) // (iters + 2))}
+    out = {"case": "HomomRLWR.hs evaluation chain (mulPublic, 5 tunnel hops, 8 mul_ pipelines, TrivGad)", "B": B, "ms": ms,
+           "evaluations_per_s": B / (ms * 1e-3), "launches_per_call": int((lib.ab_kernel_launches() - l0) // (iters + 2))}
+    if graph:      # the same chain captured once into a CUDA graph and replayed (the entries are asynchronous on the caller's stream)
+        want = run()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            got = run()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+        out["graph_ms"] = timeit(g.replay, iters)
+    return out
 
 
 def main():
