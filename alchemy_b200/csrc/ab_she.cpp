@@ -25,8 +25,11 @@ static int64_t chunk_of(int64_t batch, int64_t bytes_per_item) {
 }
 
 // digit table of the product-ring gadget over the first `nlimbs` moduli (Lol: decompose (a,b) = decompose a ++ decompose b)
-static void fill_digits(const ab_plan *p, int32_t nlimbs, int32_t base, AbMxFused &fx, bool single_limb_src) {
+static void fill_digits(const ab_plan *p, int32_t nlimbs, int32_t base, AbMxFused &fx, bool single_limb_src, int32_t src_limbs = -1) {
+    // src_limbs < nlimbs: the source is known to be ZERO in the limbs from src_limbs on (a ciphertext that was just scaled up to a
+    // larger modulus): their gadget digits are zero, contribute nothing, and are left out (a prefix of the digit list remains)
     int32_t nd = 0;
+    if (src_limbs >= 0 && src_limbs < nlimbs) nlimbs = src_limbs;
     for (int l = 0; l < nlimbs; ++l) {
         const int32_t k = ab_gadget_digits(p->q[l], base);
         uint64_t pw = 1, top = 1;                       // top = b^(k-1)
@@ -244,8 +247,15 @@ extern "C" int64_t ab_key_switch_work_bytes(const ab_plan *p, int64_t batch, int
     const int64_t fused = ks_mac_chunk(p, batch, nlimbs) * 3 * nlimbs * p->n * 8;          // c2, running sums, centred source
     return std::max(generic, fused) + (int64_t)nd * 2 * nlimbs * p->n * 8;     // + the prepared hint
 }
+static int key_switch_quad(const ab_plan *p, int64_t *out2, const int64_t *in3, const int64_t *hint, int64_t batch, int32_t nlimbs,
+                           int32_t base, void *work, void *stream, int32_t src_limbs);
 extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int64_t *in3, const int64_t *hint, int64_t batch, int32_t nlimbs,
                                       int32_t base, void *work, void *stream) {
+    return key_switch_quad(p, out2, in3, hint, batch, nlimbs, base, work, stream, nlimbs);
+}
+// src_limbs: c2 is known to vanish in the limbs from src_limbs on (see fill_digits); nlimbs = no such knowledge
+static int key_switch_quad(const ab_plan *p, int64_t *out2, const int64_t *in3, const int64_t *hint, int64_t batch, int32_t nlimbs,
+                           int32_t base, void *work, void *stream, int32_t src_limbs) {
     return ab_guard([&] {
         AB_REQUIRE(p && ((out2 && in3 && hint && work) || batch == 0), AB_ERR_ARG, "null argument");
         AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan has no CRT tables");
@@ -267,10 +277,11 @@ extern "C" int ab_key_switch_quad_dev(const ab_plan *p, int64_t *out2, const int
                 const int64_t *in = in3 + b0 * 3 * per;
                 AbMxFused fi{};
                 fi.load_mode = AB_MX_LOAD_SRC; fi.src = in + 2 * per; fi.src_ustride = 3 * per; fi.src_limb0 = 0;
-                ab_launch_crt_mixed_fused(p, AbView{c2, B, 0, nlimbs, AB_LAYOUT_PLANAR}, true, &fi, st);
+                fi.dst_ustride = per;                                  // only the limbs that can be non-zero are brought to the powerful basis
+                ab_launch_crt_mixed_fused(p, AbView{c2, B, 0, src_limbs, AB_LAYOUT_PLANAR}, true, &fi, st);
                 AbMxFused fx{};
                 fx.load_mode = AB_MX_LOAD_DIGITS;
-                fill_digits(p, nlimbs, base, fx, false);
+                fill_digits(p, nlimbs, base, fx, false, src_limbs);
                 fx.src = c2; fx.src_ustride = per; fx.n_src = (int32_t)n; fx.gK = 1;
                 if (base == 0) { fx.triv_src = in + 2 * per; fx.triv_ustride = 3 * per; }
                 AbMxMac mac{};
@@ -589,7 +600,9 @@ extern "C" int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int6
             ab_launch_ct_mul_up(p, c3, a2, b2, batch, lin, lin, (cudaStream_t)stream, prescale);
             must(ab_mod_switch_dev(p, c3h, c3, batch, 3, lin, lh, dec_mask, w, stream));
         }
-        must(ab_key_switch_quad_dev(p, c2h, c3h, hint, batch, lh, base, w, stream));
+        // after a scale-up the appended limbs of the product are exactly zero: their gadget digits vanish and are skipped
+        static const bool no_skip = getenv("AB_NO_ZERO_SKIP") && atoi(getenv("AB_NO_ZERO_SKIP")) != 0;      // A/B measurements only
+        must(key_switch_quad(p, c2h, c3h, hint, batch, lh, base, w, stream, (lh > lin && !no_skip) ? lin : lh));
         must(ab_mod_switch_dev(p, out2, c2h, batch, 2, lh, lout, dec_mask, w, stream));
     });
 }
