@@ -90,14 +90,14 @@ __device__ __forceinline__ uint32_t mx_redc_u(uint64_t T, uint32_t q, uint32_t q
 }
 // signed helpers of the WIDE path (2^30 <= q < 2^31): centred inputs and constants, signed 64-bit sums
 __device__ __forceinline__ int32_t mx_centre(uint32_t x, uint32_t q, uint32_t hq) { return (int32_t)(x > hq ? x - q : x); }      // [0,q) -> [-hq, hq]
-// signed Montgomery: T 2^-32 mod q for |T| < 2^63, result in [0,q).  qinv = q^-1 mod 2^32 = -qinv_neg.  The low words of T and m q
-// agree, so (T - m q) / 2^32 = hi(T) - hi(m q) exactly; |t| <= |T| / 2^32 + q / 2 < 2^31 by the plan's bound check (t in (-2q, 2q)).
+// signed Montgomery: T 2^-32 mod q for a signed sum T, result in [0,q).  m = lo(T) q^-1 mod 2^32 taken UNSIGNED (q^-1 = -qinv_neg): the low
+// words of T and m q agree, so (T - m q) / 2^32 = hi(T) - hi(m q) exactly, a value in (-|T|/2^32 - q, |T|/2^32].  Adding 2q makes it
+// positive and the plan's bound check keeps it below 2^32 (|T|/2^32 + 2q < 2^32), so the 32-bit arithmetic below is exact: one IMAD,
+// one IMAD.HI, one IADD3 and two conditional subtractions (a signed m needs sign tests on the result: four more instructions).
 __device__ __forceinline__ uint32_t mx_redc_s(int64_t T, uint32_t q, uint32_t qinv_neg) {
-    const int32_t m = (int32_t)((uint32_t)T * (0u - qinv_neg));
-    int32_t t = (int32_t)(T >> 32) - __mulhi(m, (int32_t)q);
-    if (t < 0) t += (int32_t)q;
-    if (t < 0) t += (int32_t)q;
-    return ab_csub((uint32_t)t, q);
+    const uint32_t m = (uint32_t)T * (0u - qinv_neg);
+    const uint32_t t = (uint32_t)(T >> 32) - __umulhi(m, q) + 2u * q;      // in (0, 3q) as an integer
+    return ab_csub(ab_csub(t, 2u * q), q);
 }
 
 template <int P, int V, bool WIDE, bool CONTIG = false>

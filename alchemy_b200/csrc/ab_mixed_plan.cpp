@@ -380,7 +380,7 @@ void ab_build_mixed(ab_plan *pl) {
         pl->mx_tab_inv[l] = di;
         // accumulator bounds of the kernel.  narrow: P (q-1)^2 + (2^32 - 1) q < 2^64 and the reduced value below 4q;
         // wide: at most T = ceil(P / 2) (P > 7), P (dense) or P / 2 (pair step) signed products of centred factors per sum:
-        // T ((q-1)/2)^2 < 2^63, and the signed Montgomery result |t| <= T ((q-1)/2)^2 / 2^32 + q / 2 must fit an int32
+        // T ((q-1)/2)^2 < 2^63, and the Montgomery value hi(T) - hi(m q) + 2q (mx_redc_s) must stay inside (0, min(3q, 2^32))
         const unsigned __int128 q = (unsigned __int128)pl->q[l];
         bool ok = true;
         if (mode[l] == 1)
@@ -394,7 +394,8 @@ void ab_build_mixed(ab_plan *pl) {
                 if (s.kind == 0 || s.kind == 2) {
                     const unsigned __int128 T = s.kind == 2 ? s.span / 2 : (s.span > 7 ? (s.span + 1) / 2 : s.span), hq = (q - 1) / 2;
                     ok = ok && (T * hq * hq < ((unsigned __int128)1 << 63));
-                    ok = ok && (((T * hq * hq) >> 32) + q / 2 + 2 < ((unsigned __int128)1 << 31));
+                    ok = ok && (((T * hq * hq) >> 32) + 2 * q + 2 < ((unsigned __int128)1 << 32));      // hi(T) - hi(m q) + 2q stays in (0, 2^32)
+                    ok = ok && (((T * hq * hq) >> 32) + 2 < q);                                          // ... and below 3q: two conditional subtractions
                 }
         pl->mx_ok[l] = ok ? (uint8_t)mode[l] : 0;
     }
