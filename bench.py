@@ -148,7 +148,13 @@ def cpu_leg(m, n, moduli, target_s=10.0, steps=1, warmup=0):
         times.append(time.perf_counter() - t)
     times = times[warmup:]
     per_step = 2 * count * len(moduli)
-    return {"value": per_step * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+    # the same restatement on ONE core ([RECALL] lol-cpp itself is single-threaded), a handful of transforms
+    one = data[0][:2]
+    t = time.perf_counter()
+    plans[0].crt_many(one, threads=1)
+    plans[0].crt_many(one, inverse=True, threads=1)
+    one_core = 4 / max(1e-9, time.perf_counter() - t)
+    return {"value": per_step * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port", "value_1core": one_core,
             "sample": f"{count} ring elements x {len(moduli)} moduli, CRT+crtInv each, {len(times)} pass(es); "
                       "C restatement (oracle/alchemy_oracle.c), not lol-cpp"}, sum(times) / len(times)
 

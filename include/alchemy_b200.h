@@ -19,6 +19,9 @@
  *   - `*_dev` entries take DEVICE pointers and a CUDA stream (as void*, 0 = default stream) and
  *     are asynchronous; `*_host` entries take HOST pointers, copy in, run, copy out, and return
  *     after the result is in the host buffer (the behaviour of a `foreign import ccall` today).
+ *     The `*_dev` compute entries neither synchronise nor allocate (scratch comes from the caller, `*_work_bytes`), so a chain of
+ *     them can be captured into a CUDA graph and replayed (call each once before capturing: kernel attributes are set lazily).
+ *     Exceptions: ab_wire_pack_dev / ab_wire_unpack_dev / ab_wire_read_header return after a device-to-host read.
  *   - buffers are owned by the caller; plans own their device tables (create/destroy).
  *   - there is no CPU fallback: without a CUDA device every compute entry returns AB_ERR_CUDA.
  *
