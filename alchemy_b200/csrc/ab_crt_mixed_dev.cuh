@@ -15,7 +15,8 @@ struct MxArgs {
     struct {
         uint32_t q, qinv_neg;      // -q^-1 mod 2^32
         const uint32_t *tab;
-        int32_t wide, pad;         // table layout of this limb (ab_mixed_plan.cpp)
+        int32_t wide;              // table layout of this limb (ab_mixed_plan.cpp)
+        int32_t lazy;              // fused inner product: how many products x * h (both below q) one 64-bit sum may hold before its Montgomery step
     } limb[AB_MAX_LIMBS];
     int32_t nsteps, n, nlimbs;
     int32_t interleave, pad_il;    // grid order: 0 = limb-major (default), 1 = limbs interleaved (AB_MX_INTERLEAVE=1)
@@ -735,6 +736,13 @@ static inline void fill_mx_args(const ab_plan *p, MxArgs &args, int32_t limb0, i
         args.limb[l].qinv_neg = neg_inv32(ld.q);
         args.limb[l].tab = inverse ? p->mx_tab_inv[limb0 + l] : p->mx_tab_fwd[limb0 + l];
         args.limb[l].wide = p->mx_ok[limb0 + l] == 2;
+        {   // k (q-1)^2 + (2^32 - 1) q < 2^64 (the sum plus the Montgomery addend) and k q < 2^33 (reduced value below 3q: two conditional
+            // subtractions): 8 terms for q < 2^30, 4 for the example moduli around 1.5e9, 2 just below 2^31
+            const unsigned __int128 q = ld.q, one = 1;
+            int k = 1;
+            while (k < 8 && (unsigned __int128)(k + 1) * (q - 1) * (q - 1) + ((one << 32) - 1) * q < (one << 64) && (unsigned __int128)(k + 1) * q < (one << 33)) ++k;
+            args.limb[l].lazy = k;
+        }
         max_words = std::max(max_words, args.tab_words[args.limb[l].wide]);
     }
 }

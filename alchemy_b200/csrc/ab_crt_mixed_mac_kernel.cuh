@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_crt_mixed_mac(const __grid_const
     // consumes all of them: the running sums, the index table and the reductions are touched once per G digits, and the G
     // products per output are accumulated exactly in 64 bits (narrow moduli: terms below 2^60, G <= 8) before one Montgomery step
     const int G = ACC_SMEM ? 1 : max(1, min(mac.group, 8));
-    const int lazy_terms = wide ? 1 : 8;
+    const int lazy_terms = args.limb[limb].lazy;      // 8 for q < 2^30; 2 ... 4 above (round 1 reduced every term of a wide limb separately)
     for (int kdg = kd0; kdg < kd1; kdg += G) {
         const int gcount = min(G, kd1 - kdg);
         for (int gi = 0; gi < gcount; ++gi) {

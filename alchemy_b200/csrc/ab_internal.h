@@ -146,7 +146,7 @@ struct AbMxStep {
     uint32_t row_magic;  // mode 1: tb / rows == umulhi(tb, row_magic); mode 2: off / sdiv == umulhi(off, row_magic)
     int32_t sdiv;
     int32_t tab_off;     // uint32 words into the limb's table block, narrow layout (q < 2^30)
-    int32_t tab_off_w;   // same for the wide layout (2^30 <= q < 2^31: two constants per matrix entry)
+    int32_t tab_off_w;   // same for the wide layout (2^30 <= q < 2^31: the constants are centred representatives stored as int32; same sizes)
     int32_t flags;       // radix-2 inverse: bit0 = this group ends the axis: fold 2^-(e-1) into the last stage
     int32_t vec;         // 1 or 2 adjacent columns per work item (2: estride even, 8-byte shared-memory accesses);
                          // div_magic then divides by estride / vec
