@@ -203,7 +203,9 @@ def mul_keyswitch_leg(ab, torch, iters=5):
         ms = e0.elapsed_time(e1) / iters
         nbytes = (32 * n * lin + 16 * n * lout) * B
         out.append({"workload": f"{name}: m'={m}, n={n}, L {lin}->{lh}->{lout}, B={B}", "ops_per_s": B / (ms * 1e-3), "ms": ms,
-                    "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "launches_per_call": int((lib.ab_kernel_launches() - l0) // iters)})
+                    "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peaks()[0],
+                    "bytes_per_op": "32 n L_in + 16 n L_out (SURVEY 8d); the pipeline is 30 n-point transforms per op at level 1: instruction-bound, not HBM-bound",
+                    "launches_per_call": int((lib.ab_kernel_launches() - l0) // iters)})
     return out
 
 
