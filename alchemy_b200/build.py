@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libalchemy_b200.so")
 SOURCES = ["ab_plan.cpp", "ab_mixed_plan.cpp", "ab_abi.cpp", "ab_she.cpp", "ab_elementwise.cu", "ab_crt_generic.cu", "ab_crt_mixed.cu", "ab_crt_mixed_inv.cu", "ab_crt_mixed_mac.cu", "ab_crt_mixed_mac_smem.cu",
-           "ab_ntt_pow2.cu", "ab_symm.cu", "ab_rng.cu", "ab_mulks_pow2.cu", "ab_wire.cu"]
+           "ab_ntt_pow2.cu", "ab_symm.cu", "ab_rng.cu", "ab_mulks_pow2.cu", "ab_mulks_n256.cu", "ab_wire.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-x", "cu"]
 

@@ -299,6 +299,10 @@ void ab_launch_crt_mixed_fused(const ab_plan *p, const AbView &v, bool inverse, 
 bool ab_mulks_pow2_supported(const ab_plan *p, int32_t lin, int32_t lh, int32_t lout, int32_t base);
 void ab_launch_mulks_pow2(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
                           int32_t lin, int32_t lh, int32_t lout, cudaStream_t st, const int64_t *prescale = nullptr);
+// the same pipeline for the limb schedule of examples/Arithmetic.hs on n = 256 (2 -> 2 -> 1 limbs, TrivGad): one warp per op, transforms in registers (ab_mulks_n256.cu)
+bool ab_mulks_n256_supported(const ab_plan *p, int32_t lin, int32_t lh, int32_t lout, int32_t base);
+void ab_launch_mulks_n256(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
+                          cudaStream_t st, const int64_t *prescale = nullptr);
 bool ab_mixed_mac_supported(const ab_plan *p, int32_t nlimbs);
 int64_t ab_mixed_mac_scratch_words(const ab_plan *p, int64_t units, int32_t nlimbs);
 int32_t ab_mixed_mac_parts(const ab_plan *p, int64_t units, int32_t nlimbs, int32_t total_digits);   // how many CTAs per unit pay off

@@ -1,0 +1,191 @@
+// ab_mulks_n256.cu -- the PT2CT `mul_` pipeline  modSwitch . keySwitchQuad hint . modSwitch . (*)  of examples/Arithmetic.hs
+// (Crypto/Alchemy/Interpreter/PT2CT.hs:172-177 on the ring F512: m' = 512, n = 256, two limbs in, two-limb TrivGad hint, one limb
+// out -- SURVEY.md B.3) as ONE kernel with ONE WARP per pair of input ciphertexts and every transform in registers.
+//
+// ab_mulks_pow2.cu runs the same pipeline for any power-of-two ring as radix-2 passes over shared memory (four residues per work
+// item, a CTA barrier per pass): at n = 256 that kernel is instruction-bound -- 15 k warp instructions per op, half of them in the
+// 32 passes of its eight transforms, whose 4-byte accesses at strides 1 and 4 also cost 2.75 x the ideal shared-memory wavefronts.
+// Here a transform is 16 lanes x 16 residues with the register windows of ab_ntt_pow2.cu (two windows of four stages, one padded
+// shared-memory transpose between them), the two transforms every phase of this limb schedule has run on the two half-warps, and
+// only __syncwarp separates the phases.  The product, the running sums and the CRT form of c2 never leave registers.
+//
+//   lanes 0-15 = limb 0, lanes 16-31 = limb 1 (until the rescale); "strided" = lane t holds positions t + 16 i, "contiguous" = 16 t + i
+//   A  (c0, c1, c2) = (a0 b0, a0 b1 + a1 b0, a1 b1) times the caller's toMSD scalar        strided, straight from HBM
+//   C  c2 -> powerful basis (inverse windows 1, 0); the halves swap them through shared memory; digit = centred lift of the OTHER
+//      limb reduced into this one -> forward windows 0, 1; (c0, c1) += digit * hint_other + c2 * hint_own                strided
+//   D  drop limb 1: its c0 / c1 go to the two halves, inverse transform, centred lift into q0, forward transform in limb 0,
+//      out = (c - x) q1^-1                                                                  strided, straight to HBM
+// Same arithmetic as the launch sequence and as ab_mulks_pow2.cu: results are bit-identical (tests/test_gpu_she.py).
+#include <algorithm>
+#include <cstdlib>
+
+#include "ab_ntt_pow2_dev.cuh"
+
+namespace {
+
+constexpr int LOGN = 8, LOGE = 4, N = 1 << LOGN, E = 1 << LOGE, PADN = N + (N >> 5), OPS = 4;      // OPS warps (ops) per CTA
+
+struct M256Args {
+    Pow2Limb fwd[2], inv[2];          // window-packed twiddles of the two limbs, both directions
+    uint64_t mu[2];                   // Barrett constants
+    uint32_t up[2], up_s[2];          // per-limb scalar of the product (the caller's toMSD factor), Shoup pair
+    uint32_t d1inv, d1inv_s;          // q1^-1 mod q0
+    int32_t scaled, pad;
+    int64_t batch;
+};
+
+#define M256_FW(W, lp, low) fwd_window<LOGE, W, ab_pow2_s(LOGN, LOGE, W), ab_pow2_lb0(LOGN, LOGE, W), true>(x, lp, lp.tw, ab_pow2_base(LOGN, LOGE, W), low, lp.q)
+#define M256_IW(W, lp, low) inv_window<LOGE, W, ab_pow2_s(LOGN, LOGE, W), ab_pow2_lb0(LOGN, LOGE, W), true>(x, lp, lp.tw, ab_pow2_base(LOGN, LOGE, W), low, lp.q)
+
+// contiguous (fully reduced or below 4q) -> strided, below 4q.  T: this half-warp's transpose buffer
+__device__ __forceinline__ void ntt_fwd(uint32_t (&x)[E], const Pow2Limb &lp, uint32_t *T, int tl) {
+    M256_FW(0, lp, 0);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) T[phys(16 * tl + i)] = x[i];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = T[phys(tl + 16 * i)];
+    M256_FW(1, lp, tl);
+}
+// strided (below 2q) -> contiguous, below 2q, scaled by n^-1
+__device__ __forceinline__ void ntt_inv(uint32_t (&x)[E], const Pow2Limb &lp, uint32_t *T, int tl) {
+    M256_IW(1, lp, tl);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) T[phys(tl + 16 * i)] = x[i];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = T[phys(16 * tl + i)];
+    M256_IW(0, lp, 0);
+}
+// centred lift of v mod qs, reduced into q
+__device__ __forceinline__ uint32_t lift_into(uint32_t v, uint32_t qs, uint32_t q) {
+    const int32_t c = ab_center(v, qs);
+    uint32_t m = c < 0 ? (uint32_t)(-c) : (uint32_t)c;
+    if (m >= q) { m -= q; if (m >= q) m %= q; }
+    return (c < 0 && m) ? q - m : m;
+}
+
+__global__ void __launch_bounds__(32 * OPS) k_mulks_n256(const __grid_constant__ M256Args a, int64_t *__restrict__ out2, const int64_t *__restrict__ a2,
+                                                         const int64_t *__restrict__ b2, const int64_t *__restrict__ hint) {
+    __shared__ uint32_t smem[OPS][4][PADN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, tl = lane & 15;
+    const int64_t b = (int64_t)blockIdx.x * OPS + warp;
+    if (b >= a.batch) return;                                   // whole warps only: the phases below synchronise per warp
+    uint32_t *T = smem[warp][half], *PW = smem[warp][2 + half], *PWo = smem[warp][2 + (half ^ 1)];
+    const int l = half;                                         // this half-warp's limb in phases A and C
+    const uint32_t q = a.fwd[l].q, qo = a.fwd[l ^ 1].q;
+    const uint64_t mu = a.mu[l];
+
+    // ---- A: product in the secret, strided layout, straight from HBM
+    uint32_t c0[E], c1[E], c2[E], x[E];
+    {
+        const int64_t *ap = a2 + (b * 2 * 2 + l) * N, *bp = b2 + (b * 2 * 2 + l) * N;      // [b][poly][limb][j]; poly 1 is 2 N further
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int j = tl + 16 * i;
+            const uint32_t a0 = (uint32_t)__ldcs(ap + j), a1 = (uint32_t)__ldcs(ap + 2 * N + j);
+            const uint32_t b0 = (uint32_t)__ldcs(bp + j), b1 = (uint32_t)__ldcs(bp + 2 * N + j);
+            uint32_t p0 = ab_mulmod(a0, b0, q, mu);
+            uint32_t p1 = ab_addmod(ab_mulmod(a0, b1, q, mu), ab_mulmod(a1, b0, q, mu), q);
+            uint32_t p2 = ab_mulmod(a1, b1, q, mu);
+            if (a.scaled) {
+                p0 = ab_shoup(p0, a.up[l], a.up_s[l], q);
+                p1 = ab_shoup(p1, a.up[l], a.up_s[l], q);
+                p2 = ab_shoup(p2, a.up[l], a.up_s[l], q);
+            }
+            c0[i] = p0; c1[i] = p1; c2[i] = p2; x[i] = p2;
+        }
+    }
+
+    // ---- C: c2 to the powerful basis in both limbs; each half takes the other's coefficients as its gadget digit (TrivGad)
+    ntt_inv(x, a.inv[l], T, tl);
+#pragma unroll
+    for (int i = 0; i < E; ++i) PW[phys(16 * tl + i)] = ab_csub(x[i], q);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = lift_into(PWo[phys(16 * tl + i)], qo, q);
+    ntt_fwd(x, a.fwd[l], T, tl);
+    {
+        // hint[d][component][limb][j]: the digit of the other limb (d = l ^ 1) and this limb's own (d = l: its transform is c2 itself)
+        const int64_t *ho = hint + ((int64_t)((l ^ 1) * 2) * 2 + l) * N, *ht = hint + ((int64_t)(l * 2) * 2 + l) * N;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int j = tl + 16 * i;
+            const uint32_t d = ab_csub(ab_csub(x[i], 2 * q), q);
+            const uint32_t h0o = (uint32_t)__ldg(ho + j), h1o = (uint32_t)__ldg(ho + 2 * N + j);
+            const uint32_t h0t = (uint32_t)__ldg(ht + j), h1t = (uint32_t)__ldg(ht + 2 * N + j);
+            c0[i] = ab_addmod(c0[i], ab_addmod(ab_mulmod(d, h0o, q, mu), ab_mulmod(c2[i], h0t, q, mu), q), q);
+            c1[i] = ab_addmod(c1[i], ab_addmod(ab_mulmod(d, h1o, q, mu), ab_mulmod(c2[i], h1t, q, mu), q), q);
+        }
+    }
+
+    // ---- D: drop limb 1.  Half 1 hands its c0 to half 0 and keeps its c1: both halves now work on one polynomial of limb 1
+    __syncwarp();
+    if (half == 1) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) PW[phys(tl + 16 * i)] = c0[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = half == 0 ? PWo[phys(tl + 16 * i)] : c1[i];
+    const uint32_t q0 = a.fwd[0].q, q1 = a.fwd[1].q;
+    ntt_inv(x, a.inv[1], T, tl);
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = lift_into(ab_csub(x[i], q1), q1, q0);
+    ntt_fwd(x, a.fwd[0], T, tl);
+    // half 0 keeps c0 of limb 0, half 1 needs c1 of limb 0 (in half 0's registers)
+    __syncwarp();
+    if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) PW[phys(tl + 16 * i)] = c1[i];
+    }
+    __syncwarp();
+    int64_t *op = out2 + (b * 2 + half) * N;                    // [b][poly][1 limb][j]
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const uint32_t cc = half == 0 ? c0[i] : PWo[phys(tl + 16 * i)];
+        const uint32_t corr = ab_csub(ab_csub(x[i], 2 * q0), q0);
+        __stcs(op + tl + 16 * i, (int64_t)ab_shoup(ab_submod(cc, corr, q0), a.d1inv, a.d1inv_s, q0));
+    }
+}
+
+}   // namespace
+
+bool ab_mulks_n256_supported(const ab_plan *p, int32_t lin, int32_t lh, int32_t lout, int32_t base) {
+    static const bool off = (getenv("AB_NO_MULKS256") && atoi(getenv("AB_NO_MULKS256")) != 0) ||
+                            (getenv("AB_NO_MULKS") && atoi(getenv("AB_NO_MULKS")) != 0);      // A/B measurements only
+    if (off || !p->pow2 || !p->has_crt || p->logn != LOGN || base != 0 || lin != 2 || lh != 2 || lout != 1 || p->L < 2) return false;
+    for (int l = 0; l < 2; ++l)
+        if (p->limb[l].q >= (1u << 30) || !p->limb[l].tw_fwd || !p->limb[l].tw_inv) return false;      // Harvey butterflies
+    return ab_pow2_loge(LOGN) == LOGE;
+}
+
+void ab_launch_mulks_n256(const ab_plan *p, int64_t *out2, const int64_t *a2, const int64_t *b2, const int64_t *hint, int64_t batch,
+                          cudaStream_t st, const int64_t *prescale) {
+    AB_REQUIRE(ab_mulks_n256_supported(p, 2, 2, 1, 0), AB_ERR_UNSUPPORTED, "n = 256 mul + key switch kernel: not supported for this plan");
+    if (batch == 0) return;
+    M256Args a{};
+    a.batch = batch;
+    a.scaled = prescale ? 1 : 0;
+    for (int l = 0; l < 2; ++l) {
+        const AbLimbDev &ld = p->limb[l];
+        const uint64_t q = (uint64_t)p->q[l];
+        for (int dir = 0; dir < 2; ++dir) {
+            Pow2Limb &pl = dir ? a.inv[l] : a.fwd[l];
+            pl.q = ld.q; pl.ninv = ld.ninv; pl.ninv_s = ld.ninv_s;
+            pl.tw = reinterpret_cast<const uint2 *>(dir ? ld.tw_inv : ld.tw_fwd);
+            const uint2_ *t0 = dir ? ld.tw0_inv : ld.tw0_fwd;
+            for (int k = 0; k < 32; ++k) pl.tw0[k] = make_uint2(t0[k].x, t0[k].y);
+        }
+        a.mu[l] = ld.mu;
+        const uint64_t up = prescale ? (uint64_t)(((prescale[l] % (int64_t)q) + (int64_t)q) % (int64_t)q) : 1;
+        a.up[l] = (uint32_t)up; a.up_s[l] = abh::shoup(up, q);
+    }
+    const uint64_t q0 = (uint64_t)p->q[0], inv = abh::invmod((uint64_t)p->q[1] % q0, q0);
+    a.d1inv = (uint32_t)inv; a.d1inv_s = abh::shoup(inv, q0);
+    k_mulks_n256<<<(unsigned)((batch + OPS - 1) / OPS), 32 * OPS, 0, st>>>(a, out2, a2, b2, hint);
+    ab_count_launch();
+    ab_check_launch("mulks_n256");
+}

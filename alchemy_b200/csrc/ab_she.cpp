@@ -571,7 +571,7 @@ static int64_t mks_inter_words(const ab_plan *p, int64_t batch, int32_t lin, int
 }
 extern "C" int64_t ab_mul_key_switch_work_bytes(const ab_plan *p, int64_t batch, int32_t lin, int32_t lh, int32_t lout, int32_t base) {
     if (!p || batch < 0 || lin < 1 || lh < 1 || lout < 1 || lin > p->L || lh > p->L || lout > p->L) return -1;
-    if (ab_mulks_pow2_supported(p, lin, lh, lout, base)) return 16;
+    if (ab_mulks_n256_supported(p, lin, lh, lout, base) || ab_mulks_pow2_supported(p, lin, lh, lout, base)) return 16;
     const int64_t w1 = ab_mod_switch_work_bytes(p, batch, 3, lin, lh), w2 = ab_key_switch_work_bytes(p, batch, lh, base),
                   w3 = ab_mod_switch_work_bytes(p, batch, 2, lh, lout);
     if (w1 < 0 || w2 < 0 || w3 < 0) return -1;
@@ -584,6 +584,10 @@ extern "C" int ab_mul_key_switch_dev(const ab_plan *p, int64_t *out2, const int6
         AB_REQUIRE(p->has_crt, AB_ERR_NO_ROOT, "plan has no CRT tables");
         AB_REQUIRE(batch >= 0 && lin >= 1 && lh >= 1 && lout >= 1 && lin <= p->L && lh <= p->L && lout <= p->L, AB_ERR_ARG, "bad batch or limb counts");
         if (batch == 0) return;
+        if (ab_mulks_n256_supported(p, lin, lh, lout, base)) {
+            ab_launch_mulks_n256(p, out2, a2, b2, hint, batch, (cudaStream_t)stream, prescale);      // examples/Arithmetic.hs: one warp per op
+            return;
+        }
         if (ab_mulks_pow2_supported(p, lin, lh, lout, base)) {
             ab_launch_mulks_pow2(p, out2, a2, b2, hint, batch, lin, lh, lout, (cudaStream_t)stream, prescale);      // no odd prime: Dec = Pow
             return;

@@ -232,7 +232,7 @@ def test_empty_batches_and_bad_arguments_of_the_fused_entries():
         ab.GT.divGPow(p9, y)
 
 
-@pytest.mark.parametrize("switch", ["AB_NO_FUSE=1", "AB_NO_MAC=1", "AB_NO_BITS=1", "AB_NO_MULTIDROP=1", "AB_NO_MULKS=1", "AB_MX_MAC_PARTS=5", "AB_MX_T=128", "AB_MX_MAC_T=256",
+@pytest.mark.parametrize("switch", ["AB_NO_FUSE=1", "AB_NO_MAC=1", "AB_NO_BITS=1", "AB_NO_MULTIDROP=1", "AB_NO_MULKS=1", "AB_NO_MULKS256=1", "AB_MX_MAC_PARTS=5", "AB_MX_T=128", "AB_MX_MAC_T=256",
                                     "AB_NO_SUBRING=1", "AB_MX_MAC_GROUP=1", "AB_MX_MAC_GROUP=3"])
 def test_every_kernel_variant_computes_the_same_bits(switch):
     """the A/B switches of DESIGN.md section 5 select alternative kernels / launch sequences; each must pass the same parity tests
@@ -247,6 +247,31 @@ def test_every_kernel_variant_computes_the_same_bits(switch):
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_she.py"), "-x", "-q", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_arithmetic_mul_one_warp_kernel_on_a_ragged_batch():
+    """examples/Arithmetic.hs `mul_` (n = 256, limbs 2 -> 2 -> 1) runs as one warp per op (ab_mulks_n256.cu): a batch that does not
+    fill the last CTA, against the stage-by-stage calls (themselves checked against the CPU restatement above)"""
+    import torch
+
+    import alchemy_b200 as ab
+    from alchemy_b200 import she
+    rng = np.random.default_rng(256)
+    plan = ab.Plan(512, ARITH_Q)
+    n, B = plan.n, 4099
+    a, b, hint = dev(rand(rng, (B, 2), ARITH_Q[:2], n)), dev(rand(rng, (B, 2), ARITH_Q[:2], n)), dev(rand(rng, (2, 2), ARITH_Q[:2], n))
+    for pre in (None, [pow(7, -1, q) for q in ARITH_Q[:2]]):
+        c3 = she.ctMul(plan, a, b)
+        if pre is not None:
+            ab.GT.scalarMul(plan, c3.reshape(B * 3, 2, n), pre, nlimbs=2)
+        want = she.modSwitch(plan, she.keySwitchQuadCirc(plan, c3, hint, 0), 1, 1)
+        got = she.mulKeySwitch(plan, a, b, hint, 2, 1, 0, prescale=pre, dec_mask=1)
+        assert torch.equal(got, want)
+    # extreme residues: 0 and q - 1 everywhere
+    top = torch.tensor([q - 1 for q in ARITH_Q[:2]], dtype=torch.int64, device="cuda").reshape(1, 1, 2, 1).expand(5, 2, 2, n).contiguous()
+    for x, y in ((top, top), (torch.zeros_like(top), top)):
+        want = she.modSwitch(plan, she.keySwitchQuadCirc(plan, she.ctMul(plan, x, y), top[:2].contiguous(), 0), 1, 0)
+        assert torch.equal(she.mulKeySwitch(plan, x, y, top[:2].contiguous(), 2, 1, 0), want)
 
 
 def test_chains_replay_from_a_cuda_graph():
