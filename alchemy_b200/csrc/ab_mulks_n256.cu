@@ -7,7 +7,9 @@
 // 32 passes of its eight transforms, whose 4-byte accesses at strides 1 and 4 also cost 2.75 x the ideal shared-memory wavefronts.
 // Here a transform is 16 lanes x 16 residues with the register windows of ab_ntt_pow2.cu (two windows of four stages, one padded
 // shared-memory transpose between them), the two transforms every phase of this limb schedule has run on the two half-warps, and
-// only __syncwarp separates the phases.  The product, the running sums and the CRT form of c2 never leave registers.
+// only __syncwarp separates the phases.  General products are Montgomery (one 64-bit multiply-add chain and one reduction per
+// sum of two products; the stray 2^-32 leaves with the caller's toMSD scalar), (c0, c1) wait in a per-lane shared-memory stash while
+// the transforms run, so that the kernel fits 80 registers and 24 warps per SM.
 //
 //   lanes 0-15 = limb 0, lanes 16-31 = limb 1 (until the rescale); "strided" = lane t holds positions t + 16 i, "contiguous" = 16 t + i
 //   A  (c0, c1, c2) = (a0 b0, a0 b1 + a1 b0, a1 b1) times the caller's toMSD scalar        strided, straight from HBM
@@ -24,13 +26,22 @@
 namespace {
 
 constexpr int LOGN = 8, LOGE = 4, N = 1 << LOGN, E = 1 << LOGE, PADN = N + (N >> 5), OPS = 4;      // OPS warps (ops) per CTA
+#ifndef AB_M256_MINB
+#define AB_M256_MINB 6
+#endif
+constexpr int MINB = AB_M256_MINB;                                                                 // CTAs per SM the register budget is cut for
 
+struct M256Limb {
+    uint32_t qinv;                    // q^-1 mod 2^32 (Montgomery)
+    uint32_t qrec;                    // floor(2^32 / q): one-multiplication reduction of a lifted digit
+    uint32_t r, r_s;                  // R = 2^32 mod q, Shoup pair: plain -> Montgomery form
+    uint32_t upr, upr_s;              // (toMSD scalar) * R: Montgomery product -> plain, scaled
+    uint32_t upr2, upr2_s;            // (toMSD scalar) * R^2: Montgomery product -> Montgomery form, scaled
+};
 struct M256Args {
     Pow2Limb fwd[2], inv[2];          // window-packed twiddles of the two limbs, both directions
-    uint64_t mu[2];                   // Barrett constants
-    uint32_t up[2], up_s[2];          // per-limb scalar of the product (the caller's toMSD factor), Shoup pair
+    M256Limb k[2];
     uint32_t d1inv, d1inv_s;          // q1^-1 mod q0
-    int32_t scaled, pad;
     int64_t batch;
 };
 
@@ -59,27 +70,36 @@ __device__ __forceinline__ void ntt_inv(uint32_t (&x)[E], const Pow2Limb &lp, ui
     for (int i = 0; i < E; ++i) x[i] = T[phys(16 * tl + i)];
     M256_IW(0, lp, 0);
 }
-// centred lift of v mod qs, reduced into q
-__device__ __forceinline__ uint32_t lift_into(uint32_t v, uint32_t qs, uint32_t q) {
+// centred lift of v mod qs (below 2^30), reduced into q: |lift| < 2^29, and floor(|lift| * qrec / 2^32) misses the quotient by at most one
+__device__ __forceinline__ uint32_t lift_into(uint32_t v, uint32_t qs, uint32_t q, uint32_t qrec) {
     const int32_t c = ab_center(v, qs);
-    uint32_t m = c < 0 ? (uint32_t)(-c) : (uint32_t)c;
-    if (m >= q) { m -= q; if (m >= q) m %= q; }
-    return (c < 0 && m) ? q - m : m;
+    const uint32_t m = c < 0 ? (uint32_t)(-c) : (uint32_t)c;
+    const uint32_t r = ab_csub(m - __umulhi(m, qrec) * q, q);
+    return (c < 0 && r) ? q - r : r;
+}
+// Montgomery reduction: T 2^-32 mod q in [0, q) for T < q 2^32
+__device__ __forceinline__ uint32_t redc(uint64_t T, uint32_t q, uint32_t qinv) {
+    const uint32_t t = (uint32_t)(T >> 32) - __umulhi((uint32_t)T * qinv, q);
+    return min(t, t + q);
 }
 
-__global__ void __launch_bounds__(32 * OPS) k_mulks_n256(const __grid_constant__ M256Args a, int64_t *__restrict__ out2, const int64_t *__restrict__ a2,
-                                                         const int64_t *__restrict__ b2, const int64_t *__restrict__ hint) {
-    __shared__ uint32_t smem[OPS][4][PADN];
+__global__ void __launch_bounds__(32 * OPS, MINB) k_mulks_n256(const __grid_constant__ M256Args a, int64_t *__restrict__ out2, const int64_t *__restrict__ a2,
+                                                               const int64_t *__restrict__ b2, const int64_t *__restrict__ hint) {
+    // per warp: a transpose / exchange buffer per half-warp, and the stash of (c0, c1) at [polynomial][i][lane]: a lane only ever
+    // touches its own column, except where the two halves hand each other a polynomial in phase D
+    __shared__ uint32_t s_t[OPS][2][PADN];
+    __shared__ uint32_t s_c[OPS][2][E][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, tl = lane & 15;
     const int64_t b = (int64_t)blockIdx.x * OPS + warp;
     if (b >= a.batch) return;                                   // whole warps only: the phases below synchronise per warp
-    uint32_t *T = smem[warp][half], *PW = smem[warp][2 + half], *PWo = smem[warp][2 + (half ^ 1)];
+    uint32_t *T = s_t[warp][half], *To = s_t[warp][half ^ 1];
+    uint32_t (*C)[E][32] = s_c[warp];
     const int l = half;                                         // this half-warp's limb in phases A and C
     const uint32_t q = a.fwd[l].q, qo = a.fwd[l ^ 1].q;
-    const uint64_t mu = a.mu[l];
+    const M256Limb &kl = a.k[l];
 
-    // ---- A: product in the secret, strided layout, straight from HBM
-    uint32_t c0[E], c1[E], c2[E], x[E];
+    // ---- A: product in the secret, strided layout, straight from HBM; Montgomery products, the stray 2^-32 leaves with the toMSD scalar
+    uint32_t c2m[E], x[E];                                      // c2 in Montgomery form (for the inner product) and plain (to be decomposed)
     {
         const int64_t *ap = a2 + (b * 2 * 2 + l) * N, *bp = b2 + (b * 2 * 2 + l) * N;      // [b][poly][limb][j]; poly 1 is 2 N further
 #pragma unroll
@@ -87,25 +107,24 @@ __global__ void __launch_bounds__(32 * OPS) k_mulks_n256(const __grid_constant__
             const int j = tl + 16 * i;
             const uint32_t a0 = (uint32_t)__ldcs(ap + j), a1 = (uint32_t)__ldcs(ap + 2 * N + j);
             const uint32_t b0 = (uint32_t)__ldcs(bp + j), b1 = (uint32_t)__ldcs(bp + 2 * N + j);
-            uint32_t p0 = ab_mulmod(a0, b0, q, mu);
-            uint32_t p1 = ab_addmod(ab_mulmod(a0, b1, q, mu), ab_mulmod(a1, b0, q, mu), q);
-            uint32_t p2 = ab_mulmod(a1, b1, q, mu);
-            if (a.scaled) {
-                p0 = ab_shoup(p0, a.up[l], a.up_s[l], q);
-                p1 = ab_shoup(p1, a.up[l], a.up_s[l], q);
-                p2 = ab_shoup(p2, a.up[l], a.up_s[l], q);
-            }
-            c0[i] = p0; c1[i] = p1; c2[i] = p2; x[i] = p2;
+            const uint32_t p0 = redc((uint64_t)a0 * b0, q, kl.qinv);
+            const uint32_t p1 = redc((uint64_t)a0 * b1 + (uint64_t)a1 * b0, q, kl.qinv);      // 2 q^2 < q 2^32
+            const uint32_t p2 = redc((uint64_t)a1 * b1, q, kl.qinv);
+            C[0][i][lane] = ab_shoup(p0, kl.upr, kl.upr_s, q);
+            C[1][i][lane] = ab_shoup(p1, kl.upr, kl.upr_s, q);
+            x[i] = ab_shoup(p2, kl.upr, kl.upr_s, q);
+            c2m[i] = ab_shoup(p2, kl.upr2, kl.upr2_s, q);
         }
     }
 
     // ---- C: c2 to the powerful basis in both limbs; each half takes the other's coefficients as its gadget digit (TrivGad)
     ntt_inv(x, a.inv[l], T, tl);
-#pragma unroll
-    for (int i = 0; i < E; ++i) PW[phys(16 * tl + i)] = ab_csub(x[i], q);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = lift_into(PWo[phys(16 * tl + i)], qo, q);
+    for (int i = 0; i < E; ++i) T[phys(16 * tl + i)] = ab_csub(x[i], q);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = lift_into(To[phys(16 * tl + i)], qo, q, kl.qrec);
     ntt_fwd(x, a.fwd[l], T, tl);
     {
         // hint[d][component][limb][j]: the digit of the other limb (d = l ^ 1) and this limb's own (d = l: its transform is c2 itself)
@@ -113,39 +132,27 @@ __global__ void __launch_bounds__(32 * OPS) k_mulks_n256(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < E; ++i) {
             const int j = tl + 16 * i;
-            const uint32_t d = ab_csub(ab_csub(x[i], 2 * q), q);
+            const uint32_t d = ab_shoup(x[i], kl.r, kl.r_s, q);                  // any 32-bit input; the digit in Montgomery form
             const uint32_t h0o = (uint32_t)__ldg(ho + j), h1o = (uint32_t)__ldg(ho + 2 * N + j);
             const uint32_t h0t = (uint32_t)__ldg(ht + j), h1t = (uint32_t)__ldg(ht + 2 * N + j);
-            c0[i] = ab_addmod(c0[i], ab_addmod(ab_mulmod(d, h0o, q, mu), ab_mulmod(c2[i], h0t, q, mu), q), q);
-            c1[i] = ab_addmod(c1[i], ab_addmod(ab_mulmod(d, h1o, q, mu), ab_mulmod(c2[i], h1t, q, mu), q), q);
+            C[0][i][lane] = ab_addmod(C[0][i][lane], redc((uint64_t)d * h0o + (uint64_t)c2m[i] * h0t, q, kl.qinv), q);
+            C[1][i][lane] = ab_addmod(C[1][i][lane], redc((uint64_t)d * h1o + (uint64_t)c2m[i] * h1t, q, kl.qinv), q);
         }
     }
 
-    // ---- D: drop limb 1.  Half 1 hands its c0 to half 0 and keeps its c1: both halves now work on one polynomial of limb 1
-    __syncwarp();
-    if (half == 1) {
-#pragma unroll
-        for (int i = 0; i < E; ++i) PW[phys(tl + 16 * i)] = c0[i];
-    }
+    // ---- D: drop limb 1.  Half 0 takes c0 of limb 1 from half 1's columns, half 1 keeps its c1: each half rounds one polynomial
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = half == 0 ? PWo[phys(tl + 16 * i)] : c1[i];
+    for (int i = 0; i < E; ++i) x[i] = C[half][i][16 + tl];
     const uint32_t q0 = a.fwd[0].q, q1 = a.fwd[1].q;
     ntt_inv(x, a.inv[1], T, tl);
 #pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = lift_into(ab_csub(x[i], q1), q1, q0);
+    for (int i = 0; i < E; ++i) x[i] = lift_into(ab_csub(x[i], q1), q1, q0, a.k[0].qrec);
     ntt_fwd(x, a.fwd[0], T, tl);
-    // half 0 keeps c0 of limb 0, half 1 needs c1 of limb 0 (in half 0's registers)
-    __syncwarp();
-    if (half == 0) {
-#pragma unroll
-        for (int i = 0; i < E; ++i) PW[phys(tl + 16 * i)] = c1[i];
-    }
-    __syncwarp();
     int64_t *op = out2 + (b * 2 + half) * N;                    // [b][poly][1 limb][j]
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-        const uint32_t cc = half == 0 ? c0[i] : PWo[phys(tl + 16 * i)];
+        const uint32_t cc = C[half][i][tl];                     // limb 0: polynomial `half` sits in half 0's columns
         const uint32_t corr = ab_csub(ab_csub(x[i], 2 * q0), q0);
         __stcs(op + tl + 16 * i, (int64_t)ab_shoup(ab_submod(cc, corr, q0), a.d1inv, a.d1inv_s, q0));
     }
@@ -168,7 +175,6 @@ void ab_launch_mulks_n256(const ab_plan *p, int64_t *out2, const int64_t *a2, co
     if (batch == 0) return;
     M256Args a{};
     a.batch = batch;
-    a.scaled = prescale ? 1 : 0;
     for (int l = 0; l < 2; ++l) {
         const AbLimbDev &ld = p->limb[l];
         const uint64_t q = (uint64_t)p->q[l];
@@ -179,9 +185,16 @@ void ab_launch_mulks_n256(const ab_plan *p, int64_t *out2, const int64_t *a2, co
             const uint2_ *t0 = dir ? ld.tw0_inv : ld.tw0_fwd;
             for (int k = 0; k < 32; ++k) pl.tw0[k] = make_uint2(t0[k].x, t0[k].y);
         }
-        a.mu[l] = ld.mu;
+        M256Limb &k = a.k[l];
+        uint32_t qi = (uint32_t)q;                                // Newton: five steps double the correct bits from 3 to 96
+        for (int it = 0; it < 5; ++it) qi *= 2u - (uint32_t)q * qi;
+        k.qinv = qi;
+        k.qrec = (uint32_t)((1ull << 32) / q);
         const uint64_t up = prescale ? (uint64_t)(((prescale[l] % (int64_t)q) + (int64_t)q) % (int64_t)q) : 1;
-        a.up[l] = (uint32_t)up; a.up_s[l] = abh::shoup(up, q);
+        const uint64_t R = (1ull << 32) % q, upr = up * R % q, upr2 = upr * R % q;
+        k.r = (uint32_t)R; k.r_s = abh::shoup(R, q);
+        k.upr = (uint32_t)upr; k.upr_s = abh::shoup(upr, q);
+        k.upr2 = (uint32_t)upr2; k.upr2_s = abh::shoup(upr2, q);
     }
     const uint64_t q0 = (uint64_t)p->q[0], inv = abh::invmod((uint64_t)p->q[1] % q0, q0);
     a.d1inv = (uint32_t)inv; a.d1inv_s = abh::shoup(inv, q0);
