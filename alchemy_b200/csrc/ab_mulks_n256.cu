@@ -25,18 +25,21 @@
 
 namespace {
 
-constexpr int LOGN = 8, LOGE = 4, N = 1 << LOGN, E = 1 << LOGE, PADN = N + (N >> 5), OPS = 4;      // OPS warps (ops) per CTA
+constexpr int LOGN = 8, LOGE = 4, N = 1 << LOGN, E = 1 << LOGE, PADN = N + (N >> 4), OPS = 4;      // OPS warps (ops) per CTA
 #ifndef AB_M256_MINB
 #define AB_M256_MINB 6
 #endif
+#ifndef AB_M256_LDB
+#define AB_M256_LDB 4
+#endif
+constexpr int LDB = AB_M256_LDB;                                                                   // elements per lane whose loads are issued together in phase A
 constexpr int MINB = AB_M256_MINB;                                                                 // CTAs per SM the register budget is cut for
 
 struct M256Limb {
     uint32_t qinv;                    // q^-1 mod 2^32 (Montgomery)
     uint32_t qrec;                    // floor(2^32 / q): one-multiplication reduction of a lifted digit
     uint32_t r, r_s;                  // R = 2^32 mod q, Shoup pair: plain -> Montgomery form
-    uint32_t upr, upr_s;              // (toMSD scalar) * R: Montgomery product -> plain, scaled
-    uint32_t upr2, upr2_s;            // (toMSD scalar) * R^2: Montgomery product -> Montgomery form, scaled
+    uint32_t upr, upr_s;              // (toMSD scalar) * R: one factor of every product carries it, the Montgomery reduction then lands on the scaled product
 };
 struct M256Args {
     Pow2Limb fwd[2], inv[2];          // window-packed twiddles of the two limbs, both directions
@@ -48,15 +51,19 @@ struct M256Args {
 #define M256_FW(W, lp, low) fwd_window<LOGE, W, ab_pow2_s(LOGN, LOGE, W), ab_pow2_lb0(LOGN, LOGE, W), true>(x, lp, lp.tw, ab_pow2_base(LOGN, LOGE, W), low, lp.q)
 #define M256_IW(W, lp, low) inv_window<LOGE, W, ab_pow2_s(LOGN, LOGE, W), ab_pow2_lb0(LOGN, LOGE, W), true>(x, lp, lp.tw, ab_pow2_base(LOGN, LOGE, W), low, lp.q)
 
+// padding of a half-warp's 256-word buffer: one word per 16, and the two halves 16 banks apart -- the strided pattern (t + 16 i)
+// and the contiguous one (16 t + i) of one half each cover 16 distinct banks, and the other half's accesses fall on the other 16
+__device__ __forceinline__ int ph(int a) { return a + (a >> 4); }
+
 // contiguous (fully reduced or below 4q) -> strided, below 4q.  T: this half-warp's transpose buffer
 __device__ __forceinline__ void ntt_fwd(uint32_t (&x)[E], const Pow2Limb &lp, uint32_t *T, int tl) {
     M256_FW(0, lp, 0);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < E; ++i) T[phys(16 * tl + i)] = x[i];
+    for (int i = 0; i < E; ++i) T[ph(16 * tl + i)] = x[i];
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = T[phys(tl + 16 * i)];
+    for (int i = 0; i < E; ++i) x[i] = T[ph(tl + 16 * i)];
     M256_FW(1, lp, tl);
 }
 // strided (below 2q) -> contiguous, below 2q, scaled by n^-1
@@ -64,10 +71,10 @@ __device__ __forceinline__ void ntt_inv(uint32_t (&x)[E], const Pow2Limb &lp, ui
     M256_IW(1, lp, tl);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < E; ++i) T[phys(tl + 16 * i)] = x[i];
+    for (int i = 0; i < E; ++i) T[ph(tl + 16 * i)] = x[i];
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = T[phys(16 * tl + i)];
+    for (int i = 0; i < E; ++i) x[i] = T[ph(16 * tl + i)];
     M256_IW(0, lp, 0);
 }
 // centred lift of v mod qs (below 2^30), reduced into q: |lift| < 2^29, and floor(|lift| * qrec / 2^32) misses the quotient by at most one
@@ -83,78 +90,103 @@ __device__ __forceinline__ uint32_t redc(uint64_t T, uint32_t q, uint32_t qinv) 
     return min(t, t + q);
 }
 
+// The straight-line code of four 256-point transforms plus sixteen-fold unrolled element loops is 64 KB, twice the instruction cache
+// of an SM, and with 24 warps at different places instruction fetch became the first stall reason (ncu: no_instruction 3.7 per issued
+// instruction).  So: the element loops run rolled over shared memory (only the transforms need compile-time register indices), and
+// phases C and D, which are both  inverse transform -> centred lift into another modulus -> forward transform,  share one loop body.
 __global__ void __launch_bounds__(32 * OPS, MINB) k_mulks_n256(const __grid_constant__ M256Args a, int64_t *__restrict__ out2, const int64_t *__restrict__ a2,
                                                                const int64_t *__restrict__ b2, const int64_t *__restrict__ hint) {
-    // per warp: a transpose / exchange buffer per half-warp, and the stash of (c0, c1) at [polynomial][i][lane]: a lane only ever
-    // touches its own column, except where the two halves hand each other a polynomial in phase D
+    // per warp: a transpose / exchange buffer per half-warp, and the stash of (c0, c1, c2) at [polynomial][i][lane]: a lane only
+    // ever touches its own column, except where the two halves hand each other a polynomial in phase D
     __shared__ uint32_t s_t[OPS][2][PADN];
-    __shared__ uint32_t s_c[OPS][2][E][32];
+    __shared__ uint32_t s_c[OPS][3][E][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, tl = lane & 15;
-    const int64_t b = (int64_t)blockIdx.x * OPS + warp;
-    if (b >= a.batch) return;                                   // whole warps only: the phases below synchronise per warp
     uint32_t *T = s_t[warp][half], *To = s_t[warp][half ^ 1];
     uint32_t (*C)[E][32] = s_c[warp];
     const int l = half;                                         // this half-warp's limb in phases A and C
-    const uint32_t q = a.fwd[l].q, qo = a.fwd[l ^ 1].q;
-    const M256Limb &kl = a.k[l];
+    const uint32_t q = a.fwd[l].q;
+    const M256Limb kl = a.k[l];
 
-    // ---- A: product in the secret, strided layout, straight from HBM; Montgomery products, the stray 2^-32 leaves with the toMSD scalar
-    uint32_t c2m[E], x[E];                                      // c2 in Montgomery form (for the inner product) and plain (to be decomposed)
+    const int64_t b = (int64_t)blockIdx.x * OPS + warp;
+    if (b >= a.batch) return;                                   // whole warps only: the phases below synchronise per warp
+
+    // ---- A: product in the secret, strided layout, straight from HBM; Montgomery products, 2^32 rides in with the toMSD scalar
     {
-        const int64_t *ap = a2 + (b * 2 * 2 + l) * N, *bp = b2 + (b * 2 * 2 + l) * N;      // [b][poly][limb][j]; poly 1 is 2 N further
+        // residues are below 2^31: only the low word of each int64 is read (the sectors touched are the same, the registers half),
+        // LDB x 4 loads in flight per lane (4, 8 and 16 measured the same: the kernel is bound by the multiplier pipe, not by this wait)
+        const uint32_t *ap = reinterpret_cast<const uint32_t *>(a2 + (b * 2 * 2 + l) * N + tl);      // [b][poly][limb][j]; poly 1 is 2 N further
+        const uint32_t *bp = reinterpret_cast<const uint32_t *>(b2 + (b * 2 * 2 + l) * N + tl);
+#pragma unroll 1
+        for (int i0 = 0; i0 < E; i0 += LDB) {
+            uint32_t a0[LDB], a1[LDB], b0[LDB], b1[LDB];
 #pragma unroll
-        for (int i = 0; i < E; ++i) {
-            const int j = tl + 16 * i;
-            const uint32_t a0 = (uint32_t)__ldcs(ap + j), a1 = (uint32_t)__ldcs(ap + 2 * N + j);
-            const uint32_t b0 = (uint32_t)__ldcs(bp + j), b1 = (uint32_t)__ldcs(bp + 2 * N + j);
-            const uint32_t p0 = redc((uint64_t)a0 * b0, q, kl.qinv);
-            const uint32_t p1 = redc((uint64_t)a0 * b1 + (uint64_t)a1 * b0, q, kl.qinv);      // 2 q^2 < q 2^32
-            const uint32_t p2 = redc((uint64_t)a1 * b1, q, kl.qinv);
-            C[0][i][lane] = ab_shoup(p0, kl.upr, kl.upr_s, q);
-            C[1][i][lane] = ab_shoup(p1, kl.upr, kl.upr_s, q);
-            x[i] = ab_shoup(p2, kl.upr, kl.upr_s, q);
-            c2m[i] = ab_shoup(p2, kl.upr2, kl.upr2_s, q);
+            for (int k = 0; k < LDB; ++k) {
+                const int o = 2 * 16 * (i0 + k);
+                a0[k] = __ldcs(ap + o); a1[k] = __ldcs(ap + 2 * 2 * N + o);
+                b0[k] = __ldcs(bp + o); b1[k] = __ldcs(bp + 2 * 2 * N + o);
+            }
+#pragma unroll
+            for (int k = 0; k < LDB; ++k) {
+                const int i = i0 + k;
+                const uint32_t s0 = ab_shoup(a0[k], kl.upr, kl.upr_s, q), s1 = ab_shoup(a1[k], kl.upr, kl.upr_s, q);      // a * scalar * 2^32
+                C[0][i][lane] = redc((uint64_t)s0 * b0[k], q, kl.qinv);
+                C[1][i][lane] = redc((uint64_t)s0 * b1[k] + (uint64_t)s1 * b0[k], q, kl.qinv);                             // 2 q^2 < q 2^32
+                C[2][i][lane] = redc((uint64_t)s1 * b1[k], q, kl.qinv);
+            }
         }
     }
 
-    // ---- C: c2 to the powerful basis in both limbs; each half takes the other's coefficients as its gadget digit (TrivGad)
-    ntt_inv(x, a.inv[l], T, tl);
-    __syncwarp();
+    uint32_t x[E];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        // pass 0 = C: c2 to the powerful basis in both limbs; each half takes the OTHER's coefficients as its gadget digit (TrivGad)
+        // pass 1 = D: drop limb 1 -- half 0 takes c0 of limb 1 from half 1's columns, half 1 keeps its c1; both lift into limb 0
+        const int li = pass ? 1 : l, lf = pass ? 0 : l;
+        const uint32_t qi = a.inv[li].q, qs = a.inv[pass ? 1 : (l ^ 1)].q, qf = a.fwd[lf].q;
+        if (pass == 0) {
 #pragma unroll
-    for (int i = 0; i < E; ++i) T[phys(16 * tl + i)] = ab_csub(x[i], q);
-    __syncwarp();
+            for (int i = 0; i < E; ++i) x[i] = C[2][i][lane];
+        } else {
+            __syncwarp();
 #pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = lift_into(To[phys(16 * tl + i)], qo, q, kl.qrec);
-    ntt_fwd(x, a.fwd[l], T, tl);
-    {
-        // hint[d][component][limb][j]: the digit of the other limb (d = l ^ 1) and this limb's own (d = l: its transform is c2 itself)
-        const int64_t *ho = hint + ((int64_t)((l ^ 1) * 2) * 2 + l) * N, *ht = hint + ((int64_t)(l * 2) * 2 + l) * N;
+            for (int i = 0; i < E; ++i) x[i] = C[half][i][16 + tl];
+        }
+        ntt_inv(x, a.inv[li], T, tl);
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < E; ++i) {
-            const int j = tl + 16 * i;
-            const uint32_t d = ab_shoup(x[i], kl.r, kl.r_s, q);                  // any 32-bit input; the digit in Montgomery form
-            const uint32_t h0o = (uint32_t)__ldg(ho + j), h1o = (uint32_t)__ldg(ho + 2 * N + j);
-            const uint32_t h0t = (uint32_t)__ldg(ht + j), h1t = (uint32_t)__ldg(ht + 2 * N + j);
-            C[0][i][lane] = ab_addmod(C[0][i][lane], redc((uint64_t)d * h0o + (uint64_t)c2m[i] * h0t, q, kl.qinv), q);
-            C[1][i][lane] = ab_addmod(C[1][i][lane], redc((uint64_t)d * h1o + (uint64_t)c2m[i] * h1t, q, kl.qinv), q);
+        for (int i = 0; i < E; ++i) T[ph(16 * tl + i)] = ab_csub(x[i], qi);
+        __syncwarp();
+        const uint32_t *src = pass ? T : To;
+        const uint32_t qrec = a.k[lf].qrec;
+#pragma unroll
+        for (int i = 0; i < E; ++i) x[i] = lift_into(src[ph(16 * tl + i)], qs, qf, qrec);
+        ntt_fwd(x, a.fwd[lf], T, tl);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < E; ++i) T[ph(tl + 16 * i)] = x[i];                  // read back by this lane only, in the rolled loops below
+        if (pass == 0) {
+            // hint[d][component][limb][j]: the digit of the other limb (d = l ^ 1) and this limb's own (d = l: its transform is c2 itself)
+            const int64_t *ho = hint + ((int64_t)((l ^ 1) * 2) * 2 + l) * N + tl, *ht = hint + ((int64_t)(l * 2) * 2 + l) * N + tl;
+#pragma unroll 4
+            for (int i = 0; i < E; ++i) {
+                const uint32_t d = ab_shoup(T[ph(tl + 16 * i)], kl.r, kl.r_s, q);                  // any 32-bit input; the digit in Montgomery form
+                const uint32_t c2m = ab_shoup(C[2][i][lane], kl.r, kl.r_s, q);
+                const uint32_t h0o = (uint32_t)__ldg(ho + 16 * i), h1o = (uint32_t)__ldg(ho + 2 * N + 16 * i);
+                const uint32_t h0t = (uint32_t)__ldg(ht + 16 * i), h1t = (uint32_t)__ldg(ht + 2 * N + 16 * i);
+                C[0][i][lane] = ab_addmod(C[0][i][lane], redc((uint64_t)d * h0o + (uint64_t)c2m * h0t, q, kl.qinv), q);
+                C[1][i][lane] = ab_addmod(C[1][i][lane], redc((uint64_t)d * h1o + (uint64_t)c2m * h1t, q, kl.qinv), q);
+            }
         }
     }
 
-    // ---- D: drop limb 1.  Half 0 takes c0 of limb 1 from half 1's columns, half 1 keeps its c1: each half rounds one polynomial
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = C[half][i][16 + tl];
-    const uint32_t q0 = a.fwd[0].q, q1 = a.fwd[1].q;
-    ntt_inv(x, a.inv[1], T, tl);
-#pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = lift_into(ab_csub(x[i], q1), q1, q0, a.k[0].qrec);
-    ntt_fwd(x, a.fwd[0], T, tl);
-    int64_t *op = out2 + (b * 2 + half) * N;                    // [b][poly][1 limb][j]
-#pragma unroll
+    const uint32_t q0 = a.fwd[0].q;
+    int64_t *op = out2 + (b * 2 + half) * N + tl;               // [b][poly][1 limb][j]
+#pragma unroll 4
     for (int i = 0; i < E; ++i) {
         const uint32_t cc = C[half][i][tl];                     // limb 0: polynomial `half` sits in half 0's columns
-        const uint32_t corr = ab_csub(ab_csub(x[i], 2 * q0), q0);
-        __stcs(op + tl + 16 * i, (int64_t)ab_shoup(ab_submod(cc, corr, q0), a.d1inv, a.d1inv_s, q0));
+        const uint32_t xi = T[ph(tl + 16 * i)];
+        const uint32_t corr = ab_csub(ab_csub(xi, 2 * q0), q0);
+        __stcs(op + 16 * i, (int64_t)ab_shoup(ab_submod(cc, corr, q0), a.d1inv, a.d1inv_s, q0));
     }
 }
 
@@ -191,10 +223,9 @@ void ab_launch_mulks_n256(const ab_plan *p, int64_t *out2, const int64_t *a2, co
         k.qinv = qi;
         k.qrec = (uint32_t)((1ull << 32) / q);
         const uint64_t up = prescale ? (uint64_t)(((prescale[l] % (int64_t)q) + (int64_t)q) % (int64_t)q) : 1;
-        const uint64_t R = (1ull << 32) % q, upr = up * R % q, upr2 = upr * R % q;
+        const uint64_t R = (1ull << 32) % q, upr = up * R % q;
         k.r = (uint32_t)R; k.r_s = abh::shoup(R, q);
         k.upr = (uint32_t)upr; k.upr_s = abh::shoup(upr, q);
-        k.upr2 = (uint32_t)upr2; k.upr2_s = abh::shoup(upr2, q);
     }
     const uint64_t q0 = (uint64_t)p->q[0], inv = abh::invmod((uint64_t)p->q[1] % q0, q0);
     a.d1inv = (uint32_t)inv; a.d1inv_s = abh::shoup(inv, q0);
