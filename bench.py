@@ -181,7 +181,7 @@ def mul_keyswitch_leg(ab, torch, iters=5):
     out = []
     for name, m, moduli, lin, lh, lout, B, pt in (
             ("HomomRLWR level 1", 20475, [1543651201, 689270401, 718099201, 720720001, 1556755201, 1567238401], 4, 5, 3, 1024, 32),
-            ("Arithmetic", 512, [268440577, 8392193, 1073750017], 2, 2, 1, 16384, 7)):
+            ("Arithmetic", 512, [268440577, 8392193, 1073750017], 2, 2, 1, 65536, 7)):
         plan = ab.Plan(m, moduli)
         n = plan.n
         rnd = lambda lead, L: torch.stack([torch.randint(0, q, tuple(lead) + (n,), dtype=torch.int64, device="cuda") for q in moduli[:L]], dim=-2)
@@ -204,7 +204,9 @@ def mul_keyswitch_leg(ab, torch, iters=5):
         nbytes = (32 * n * lin + 16 * n * lout) * B
         out.append({"workload": f"{name}: m'={m}, n={n}, L {lin}->{lh}->{lout}, B={B}", "ops_per_s": B / (ms * 1e-3), "ms": ms,
                     "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peaks()[0],
-                    "bytes_per_op": "32 n L_in + 16 n L_out (SURVEY 8d); the pipeline is 30 n-point transforms per op at level 1: instruction-bound, not HBM-bound",
+                    "bytes_per_op": "32 n L_in + 16 n L_out (SURVEY 8d); " + (
+                        "the pipeline is 30 n-point transforms per op at level 1: instruction-bound, not HBM-bound" if m != 512 else
+                        "8 transforms of 256 points per op in one warp (k_mulks_n256): bound by the integer-multiply pipe, not by HBM"),
                     "launches_per_call": int((lib.ab_kernel_launches() - l0) // iters)})
     return out
 
