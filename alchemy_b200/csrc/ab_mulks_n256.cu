@@ -10,7 +10,7 @@
 // only __syncwarp separates the phases.  General products are Montgomery (one 64-bit multiply-add chain and one reduction per
 // sum of two products; the factor 2^32 rides in with the caller's toMSD scalar), (c0, c1, c2) wait in a per-lane shared-memory stash
 // while the transforms run, so that the kernel fits 80 registers and 24 warps per SM.  Measured (tools/bench_she.py, 32768 ops):
-// 57.6 M ops/s on ab_mulks_pow2.cu, 148 M here; 4.0 k warp instructions per op; bound by the integer-multiply pipe.
+// 57.6 M ops/s on ab_mulks_pow2.cu, 155 M here; 4.0 k warp instructions per op; bound by the integer-multiply pipe.
 //
 //   lanes 0-15 = limb 0, lanes 16-31 = limb 1 (until the rescale); "strided" = lane t holds positions t + 16 i, "contiguous" = 16 t + i
 //   A  (c0, c1, c2) = (a0 b0, a0 b1 + a1 b0, a1 b1) times the caller's toMSD scalar        strided, straight from HBM
@@ -26,14 +26,17 @@
 
 namespace {
 
-constexpr int LOGN = 8, LOGE = 4, N = 1 << LOGN, E = 1 << LOGE, PADN = N + (N >> 4), OPS = 4;      // OPS warps (ops) per CTA
+#ifndef AB_M256_OPS
+#define AB_M256_OPS 4
+#endif
 #ifndef AB_M256_MINB
 #define AB_M256_MINB 6
 #endif
 #ifndef AB_M256_LDB
-#define AB_M256_LDB 4
+#define AB_M256_LDB 2
 #endif
-constexpr int LDB = AB_M256_LDB;                                                                   // elements per lane whose loads are issued together in phase A
+constexpr int LOGN = 8, LOGE = 4, N = 1 << LOGN, E = 1 << LOGE, PADN = N + (N >> 4), OPS = AB_M256_OPS;      // OPS warps (ops) per CTA
+constexpr int LDB = AB_M256_LDB;                                                                   // residue pairs per lane whose four 16-byte loads are issued together in phase A
 constexpr int MINB = AB_M256_MINB;                                                                 // CTAs per SM the register budget is cut for
 
 struct M256Limb {
@@ -46,7 +49,7 @@ struct M256Args {
     Pow2Limb fwd[2], inv[2];          // window-packed twiddles of the two limbs, both directions
     M256Limb k[2];
     uint32_t d1inv, d1inv_s;          // q1^-1 mod q0
-    int64_t batch;
+    int64_t batch, pf_dist;
 };
 
 #define M256_FW(W, lp, low) fwd_window<LOGE, W, ab_pow2_s(LOGN, LOGE, W), ab_pow2_lb0(LOGN, LOGE, W), true>(x, lp, lp.tw, ab_pow2_base(LOGN, LOGE, W), low, lp.q)
@@ -82,7 +85,8 @@ __device__ __forceinline__ void ntt_inv(uint32_t (&x)[E], const Pow2Limb &lp, ui
 __device__ __forceinline__ uint32_t lift_into(uint32_t v, uint32_t qs, uint32_t q, uint32_t qrec) {
     const int32_t c = ab_center(v, qs);
     const uint32_t m = c < 0 ? (uint32_t)(-c) : (uint32_t)c;
-    const uint32_t r = ab_csub(m - __umulhi(m, qrec) * q, q);
+    uint32_t r = m;
+    if (qs > 2 * q) r = ab_csub(m - __umulhi(m, qrec) * q, q);      // otherwise |lift| <= qs / 2 <= q already (uniform per half-warp)
     return (c < 0 && r) ? q - r : r;
 }
 // Montgomery reduction: T 2^-32 mod q in [0, q) for T < q 2^32
@@ -110,31 +114,47 @@ __global__ void __launch_bounds__(32 * OPS, MINB) k_mulks_n256(const __grid_cons
 
     const int64_t b = (int64_t)blockIdx.x * OPS + warp;
     if (b >= a.batch) return;                                   // whole warps only: the phases below synchronise per warp
+    // pull the inputs of an op that starts an eighth of a wave later into L2 (two 8 KB bulk prefetches per warp): +3.7 % (any distance
+    // from 0.03 to 0.25 waves measured the same, one wave nothing, two waves -9 %: the lines fall out of L2 again)
+    if (tl == 0 && b + a.pf_dist < a.batch) {
+        const int64_t *nx = (half ? b2 : a2) + (b + a.pf_dist) * (2 * 2 * N);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(2 * 2 * N * 8) : "memory");
+    }
 
-    // ---- A: product in the secret, strided layout, straight from HBM; Montgomery products, 2^32 rides in with the toMSD scalar
+    // ---- A: product in the secret, straight from HBM; Montgomery products, 2^32 rides in with the toMSD scalar
     {
-        // residues are below 2^31: only the low word of each int64 is read (the sectors touched are the same, the registers half),
-        // LDB x 4 loads in flight per lane (4, 8 and 16 measured the same: the kernel is bound by the multiplier pipe, not by this wait)
-        const uint32_t *ap = reinterpret_cast<const uint32_t *>(a2 + (b * 2 * 2 + l) * N + tl);      // [b][poly][limb][j]; poly 1 is 2 N further
-        const uint32_t *bp = reinterpret_cast<const uint32_t *>(b2 + (b * 2 * 2 + l) * N + tl);
+        // 16-byte loads: a lane takes the residue PAIRS at 2 t + 32 k, so a half-warp request is 256 contiguous bytes (with 8-byte loads
+        // at t + 16 i it was 128, and the loads, products and stores alone ran at 0.70 of the HBM peak; residues are below 2^31, only
+        // the low words are used).  The products are pointwise, so any assignment of positions to lanes will do here: they go to the
+        // stash slot of the lane that owns the position in the strided layout of the transforms, (i, lane) = (j / 16, j % 16).
+        const int4 *ap = reinterpret_cast<const int4 *>(a2 + (b * 2 * 2 + l) * N) + tl;      // [b][poly][limb][j]; poly 1 is 2 N residues further
+        const int4 *bp = reinterpret_cast<const int4 *>(b2 + (b * 2 * 2 + l) * N) + tl;
+        uint32_t *cs = &C[0][tl >> 3][16 * half + ((2 * tl) & 15)];                          // + 2 k rows; the three polynomials are E rows apart
 #pragma unroll 1
-        for (int i0 = 0; i0 < E; i0 += LDB) {
-            uint32_t a0[LDB], a1[LDB], b0[LDB], b1[LDB];
+        for (int k0 = 0; k0 < E / 2; k0 += LDB) {
+            int4 a0[LDB], a1[LDB], b0[LDB], b1[LDB];
 #pragma unroll
             for (int k = 0; k < LDB; ++k) {
-                const int o = 2 * 16 * (i0 + k);
-                a0[k] = __ldcs(ap + o); a1[k] = __ldcs(ap + 2 * 2 * N + o);
-                b0[k] = __ldcs(bp + o); b1[k] = __ldcs(bp + 2 * 2 * N + o);
+                const int o = 16 * (k0 + k);
+                a0[k] = __ldcs(ap + o); a1[k] = __ldcs(ap + N + o);
+                b0[k] = __ldcs(bp + o); b1[k] = __ldcs(bp + N + o);
             }
 #pragma unroll
             for (int k = 0; k < LDB; ++k) {
-                const int i = i0 + k;
-                const uint32_t s0 = ab_shoup(a0[k], kl.upr, kl.upr_s, q), s1 = ab_shoup(a1[k], kl.upr, kl.upr_s, q);      // a * scalar * 2^32
-                C[0][i][lane] = redc((uint64_t)s0 * b0[k], q, kl.qinv);
-                C[1][i][lane] = redc((uint64_t)s0 * b1[k] + (uint64_t)s1 * b0[k], q, kl.qinv);                             // 2 q^2 < q 2^32
-                C[2][i][lane] = redc((uint64_t)s1 * b1[k], q, kl.qinv);
+                uint32_t r[3][2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t x0 = e ? a0[k].z : a0[k].x, x1 = e ? a1[k].z : a1[k].x, y0 = e ? b0[k].z : b0[k].x, y1 = e ? b1[k].z : b1[k].x;
+                    const uint32_t s0 = ab_shoup(x0, kl.upr, kl.upr_s, q), s1 = ab_shoup(x1, kl.upr, kl.upr_s, q);      // a * scalar * 2^32
+                    r[0][e] = redc((uint64_t)s0 * y0, q, kl.qinv);
+                    r[1][e] = redc((uint64_t)s0 * y1 + (uint64_t)s1 * y0, q, kl.qinv);                                 // 2 q^2 < q 2^32
+                    r[2][e] = redc((uint64_t)s1 * y1, q, kl.qinv);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) *reinterpret_cast<uint2 *>(cs + (c * E + 2 * (k0 + k)) * 32) = make_uint2(r[c][0], r[c][1]);
             }
         }
+        __syncwarp();                                           // the stash rows were written by other lanes of the half-warp
     }
 
     uint32_t x[E];
@@ -208,6 +228,7 @@ void ab_launch_mulks_n256(const ab_plan *p, int64_t *out2, const int64_t *a2, co
     if (batch == 0) return;
     M256Args a{};
     a.batch = batch;
+    a.pf_dist = std::max<int64_t>(OPS, (int64_t)p->sm_count * MINB * OPS / 8);      // ops ahead of the one a warp works on: an eighth of a wave
     for (int l = 0; l < 2; ++l) {
         const AbLimbDev &ld = p->limb[l];
         const uint64_t q = (uint64_t)p->q[l];
