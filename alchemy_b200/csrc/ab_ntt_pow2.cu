@@ -89,6 +89,7 @@ k_crt_pow2_fwd(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
     const uint2 *__restrict__ tw = lp.tw;
     uint32_t *sm = smem + slot * C::PADN;
     int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * C::N;
+    if constexpr (C::TPC == 1 && LOGN >= 13) pow2_prefetch<LOGN>(args, y);
 
     // coalesced 16-byte loads of the block this warp owns in window 0; narrow to uint32 in smem
     {
@@ -216,6 +217,7 @@ k_crt_pow2_inv(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
     const uint2 *__restrict__ tw = lp.tw;
     uint32_t *sm = smem + slot * C::PADN;
     int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * C::N;
+    if constexpr (C::TPC == 1 && LOGN >= 13) pow2_prefetch<LOGN>(args, y);
 
     uint32_t x[E];
 #pragma unroll
@@ -272,6 +274,7 @@ k_crt_pow2_fwd_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     const uint32_t q = lp.q;
     const uint2 *__restrict__ tw = lp.tw;
     int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * (1 << LOGN);
+    pow2_c2_prefetch(args, y);
     {   // this warp's 1024-residue block of this CTA's half
         const int4 *src = reinterpret_cast<const int4 *>(yp + (int64_t)(16 * r + wb) * G * E);
 #pragma unroll
@@ -342,6 +345,7 @@ k_crt_pow2_inv_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     const uint32_t q = lp.q;
     const uint2 *__restrict__ tw = lp.tw;
     int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * (1 << LOGN);
+    pow2_c2_prefetch(args, y);
     uint32_t x[E];
 #if AB_POW2_RELAXED_ARRIVE_INV
     asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // "I am running": no data to publish
@@ -400,6 +404,11 @@ static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool 
     using C = Pow2Cfg<LOGN, LOGE>;
     const size_t smem = (size_t)C::TPC * C::PADN * sizeof(uint32_t);
     const dim3 grid((unsigned)((args.batch + C::TPC - 1) / C::TPC), (unsigned)args.nlimbs);
+    // L2 prefetch distance of the large transforms, in resident waves of CTAs (0.125 ... 0.5 measured the same at n = 32768: 0.612 -> 0.629 of
+    // the HBM roofline; one wave ahead gains half of that, and beyond the lines fall out of L2 again); 0 switches it off
+    static const double pf_waves = getenv("AB_POW2_PF_WAVES") ? atof(getenv("AB_POW2_PF_WAVES")) : 0.25;
+    Pow2Args pa = args;
+    pa.pf_dist = (int32_t)(pf_waves * p->sm_count * ((LOGN == 15 && AB_POW2_CLUSTER) ? 2 : C::MINB));
     if constexpr (LOGN == 15 && AB_POW2_CLUSTER) {
         constexpr size_t half = ((size_t)(1 << 14) + (1 << 9)) * sizeof(uint32_t);
         static thread_local bool ready = false;
@@ -409,14 +418,14 @@ static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool 
             ready = true;
         }
         const dim3 g2((unsigned)(2 * args.batch), (unsigned)args.nlimbs);
-        if (inverse) k_crt_pow2_inv_c2<LOGE, LAZY><<<g2, 512, half, st>>>(args, y);
-        else k_crt_pow2_fwd_c2<LOGE, LAZY><<<g2, 512, half, st>>>(args, y);
+        if (inverse) k_crt_pow2_inv_c2<LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
+        else k_crt_pow2_fwd_c2<LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
     } else if (inverse) {
         auto k = k_crt_pow2_inv<LOGN, LOGE, LAZY>;
         static thread_local bool ready = false;
         if (!ready && smem > 48 * 1024) AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ready = true;
-        k<<<grid, C::THREADS, smem, st>>>(args, y);
+        k<<<grid, C::THREADS, smem, st>>>(pa, y);
     } else if constexpr (C::PIPE) {
         auto k = k_crt_pow2_fwd_pipe<LOGN, LOGE, LAZY>;
         static thread_local int per_sm = 0;
@@ -432,7 +441,7 @@ static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool 
         static thread_local bool ready = false;
         if (!ready && smem > 48 * 1024) AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ready = true;
-        k<<<grid, C::THREADS, smem, st>>>(args, y);
+        k<<<grid, C::THREADS, smem, st>>>(pa, y);
     }
     ab_count_launch();
     ab_check_launch("crt_pow2");

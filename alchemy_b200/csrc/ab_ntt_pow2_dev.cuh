@@ -17,7 +17,29 @@ struct Pow2Args {
     Pow2Limb limb[AB_MAX_LIMBS];
     int32_t nlimbs;
     int64_t batch;            // ring elements; transform (b, limb) lives at y + (b * nlimbs + limb) * N
+    int32_t pf_dist;          // cluster kernels: CTAs ahead (in launch order) whose input is pulled into L2; 0 = no prefetch
 };
+
+// 2-CTA cluster kernels (n = 32768): the half-transform that the CTA `dist` places later in launch order will load (128 KB, contiguous)
+// is requested into L2 now, 8 KB per thread of the first half-warp, so that its load phase waits on L2 instead of HBM
+__device__ __forceinline__ void pow2_c2_prefetch(const Pow2Args &args, const int64_t *y) {
+    if (args.pf_dist <= 0 || threadIdx.x >= 16) return;
+    const int64_t lin = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + args.pf_dist;
+    if (lin >= (int64_t)gridDim.x * gridDim.y) return;
+    const int64_t x2 = lin % gridDim.x, l2 = lin / gridDim.x;
+    const int64_t *src = y + ((x2 >> 1) * args.nlimbs + l2) * (1 << 15) + (x2 & 1) * (1 << 14) + threadIdx.x * 1024;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(8192) : "memory");
+}
+// the same for the one-transform-per-CTA kernels (n = 8192, 16384): the transform of the CTA `dist` places later, 8 KB per thread
+template <int LOGN>
+__device__ __forceinline__ void pow2_prefetch(const Pow2Args &args, const int64_t *y) {
+    if (args.pf_dist <= 0 || threadIdx.x >= (1 << LOGN) / 1024) return;
+    const int64_t lin = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + args.pf_dist;
+    if (lin >= (int64_t)gridDim.x * gridDim.y) return;
+    const int64_t b2 = lin % gridDim.x, l2 = lin / gridDim.x;
+    const int64_t *src = y + ((b2 * args.nlimbs + l2) << LOGN) + threadIdx.x * 1024;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(8192) : "memory");
+}
 
 template <bool LAZY>
 __device__ __forceinline__ void bf_fwd(uint32_t &X, uint32_t &Y, uint2 w, uint32_t q) {
