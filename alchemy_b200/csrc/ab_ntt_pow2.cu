@@ -39,9 +39,6 @@
                                    // barrier.cluster.arrive.relaxed instead of the default .release, which ptxas implements with MEMBAR.ALL.GPU
                                    // (measured: forward 0.520 -> 0.497 ms per launch, 0.64 -> 0.67 of the HBM roofline)
 #endif
-#ifndef AB_POW2_RELAXED_ARRIVE_INV
-#define AB_POW2_RELAXED_ARRIVE_INV 0   // the same for the "I am running" arrival of the inverse kernel measured SLOWER (0.572 -> 0.592 ms): left at .release
-#endif
 
 template <int LOGN, int LOGE>
 struct Pow2Cfg {
@@ -332,13 +329,20 @@ k_crt_pow2_fwd_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     }
 }
 
+// n = 32768 inverse WITHOUT a cluster (round 2; the 2-CTA cluster version it replaces pushed half of the first window's outputs into the
+// peer's shared memory and measured 0.566 ms per 2.147 GB launch against 0.515 ms here): the first stage of the inverse (stride 16384, one twiddle per butterfly) is the only one that
+// crosses the halves, and after it the two halves are independent 16384-point transforms.  So CTA r of a pair computes just ITS output
+// of every stride-16384 butterfly while loading -- r = 0 the sums, r = 1 the twiddled differences -- then stages 13..10 on its 16 rows of
+// the 32 x 1024 view, two columns per thread, and the remaining two windows in its own shared memory.  Both CTAs read the whole input
+// (the second reader hits L2; HBM traffic stays the algorithmic 16 bytes per residue), nothing crosses SMs, no cluster barrier and no
+// MEMBAR; the multiplications are the same in total (CTA 1 does the 16384 of stage 14, CTA 0 none).
 template <int LOGE, bool LAZY>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 2)
-k_crt_pow2_inv_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
+__global__ void __launch_bounds__(512, 2)
+k_crt_pow2_inv_h2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
     constexpr int LOGN = 15, E = 1 << LOGE, G = 32;
+    static_assert(LOGE == 5, "half kernel: stage 14, a window of 4 stages, 2 windows of 5 stages");
     extern __shared__ uint32_t sm[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned r = cluster.block_rank();
+    const unsigned r = blockIdx.x & 1;
     const int tl = threadIdx.x, wb = tl / G, lg = tl % G;
     const int64_t b = blockIdx.x >> 1;
     const Pow2Limb &lp = args.limb[blockIdx.y];
@@ -346,26 +350,37 @@ k_crt_pow2_inv_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     const uint2 *__restrict__ tw = lp.tw;
     int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * (1 << LOGN);
     pow2_c2_prefetch(args, y);
-    uint32_t x[E];
-#if AB_POW2_RELAXED_ARRIVE_INV
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // "I am running": no data to publish
-#else
-    cluster.barrier_arrive();   // "I am running": waited for just before the first store into the peer's shared memory
-#endif
-    {   // stages 14..10 on this CTA's 512 columns, straight from HBM; results scattered to both halves
-        const int low = 512 * (int)r + tl;
+    {
+        constexpr int64_t base2 = ab_pow2_base(LOGN, LOGE, 2);
 #pragma unroll
-        for (int i = 0; i < E; ++i) x[i] = (uint32_t)__ldcs(yp + low + (i << 10));
-        AB_IW(2);
-        cluster.barrier_wait();  // the peer is running
-        uint32_t *peer = cluster.map_shared_rank(sm, r ^ 1);
-        uint32_t *h0 = (r == 0) ? sm : peer, *h1 = (r == 0) ? peer : sm;
+        for (int c = 0; c < 2; ++c) {
+            const int col = tl + 512 * c;
+            uint32_t lo[16], hi[16], x16[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h0[phys(i * 1024 + low)] = x[i];
+            for (int i = 0; i < 16; ++i) {
+                lo[i] = (uint32_t)__ldcs(yp + col + (i << 10));
+                hi[i] = (uint32_t)__ldcs(yp + col + ((i + 16) << 10));
+            }
+            if (r == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h1[phys(i * 1024 + low)] = x[16 + i];
+                for (int i = 0; i < 16; ++i) x16[i] = LAZY ? ab_csub(lo[i] + hi[i], 2 * q) : ab_addmod(lo[i], hi[i], q);
+            } else {
+                // twiddle k = 16 + i of window 2 for this column: entries (k >> 1) << 10 of the packed table, two per 16-byte load
+                const uint4 *tp = reinterpret_cast<const uint4 *>(tw + base2) + col;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const uint4 pr = __ldg(tp + ((int64_t)((16 + i) >> 1) << 10));
+                    x16[i] = LAZY ? ab_shoup_lazy(lo[i] - hi[i] + 2 * q, pr.x, pr.y, q) : ab_shoup(ab_submod(lo[i], hi[i], q), pr.x, pr.y, q);
+                    x16[i + 1] = LAZY ? ab_shoup_lazy(lo[i + 1] - hi[i + 1] + 2 * q, pr.z, pr.w, q) : ab_shoup(ab_submod(lo[i + 1], hi[i + 1], q), pr.z, pr.w, q);
+                }
+            }
+            inv_window<4, 2, 10, 0, LAZY>(x16, lp, tw, base2, col, q);      // stages 13 .. 10: the first 16 twiddles of window 2
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sm[phys(i * 1024 + col)] = x16[i];
+        }
     }
-    cluster.sync();      // this half is complete (local and remote contributions)
+    __syncthreads();
+    uint32_t x[E];
 #pragma unroll
     for (int w = 1; w >= 0; --w) {
         const int S = ab_pow2_s(LOGN, LOGE, w);
@@ -414,11 +429,11 @@ static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool 
         static thread_local bool ready = false;
         if (!ready) {
             AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_fwd_c2<LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
-            AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_inv_c2<LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
+            AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_inv_h2<LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
             ready = true;
         }
         const dim3 g2((unsigned)(2 * args.batch), (unsigned)args.nlimbs);
-        if (inverse) k_crt_pow2_inv_c2<LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
+        if (inverse) k_crt_pow2_inv_h2<LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
         else k_crt_pow2_fwd_c2<LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
     } else if (inverse) {
         auto k = k_crt_pow2_inv<LOGN, LOGE, LAZY>;

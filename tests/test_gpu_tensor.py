@@ -26,7 +26,8 @@ MIXED = [(9, [19, 37]), (27, [109]), (25, [101]), (45, [181, 541]), (36, [37, 73
          # the 10-point pair step (p = 11), alone, beside 13 (stride 12: two columns per item) and over a modulus above 2^30 (signed sums)
          (11, [23, 67]), (55, [331]), (143, [859]), (1001, [1500018521, 2003])]
 # 2^30 < q < 2^31: the exact (non-lazy) butterfly path; 2147483647 = 2^31 - 1
-BIGQ = [(512, 2147483137), (2048, 2013265921), (63, 2147483647), (20475, 2147418001)]
+BIGQ = [(512, 2147483137), (2048, 2013265921), (63, 2147483647), (20475, 2147418001),
+        (32768, 2013265921), (65536, 2013265921)]       # the exact butterflies in the large kernels (n = 16384; n = 32768: cluster forward, split inverse)
 
 
 def torch_mod():
