@@ -271,7 +271,7 @@ k_crt_pow2_fwd_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     const uint32_t q = lp.q;
     const uint2 *__restrict__ tw = lp.tw;
     int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * (1 << LOGN);
-    pow2_c2_prefetch(args, y);
+    pow2_c2_prefetch<15>(args, y);
     {   // this warp's 1024-residue block of this CTA's half
         const int4 *src = reinterpret_cast<const int4 *>(yp + (int64_t)(16 * r + wb) * G * E);
 #pragma unroll
@@ -329,18 +329,19 @@ k_crt_pow2_fwd_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     }
 }
 
-// n = 32768 inverse WITHOUT a cluster (round 2; the 2-CTA cluster version it replaces pushed half of the first window's outputs into the
+// n = 32768 (and n = 16384) inverse as two independent CTAs per transform, WITHOUT a cluster (round 2; the 2-CTA cluster version it replaces pushed half of the first window's outputs into the
 // peer's shared memory and measured 0.566 ms per 2.147 GB launch against 0.515 ms here): the first stage of the inverse (stride 16384, one twiddle per butterfly) is the only one that
 // crosses the halves, and after it the two halves are independent 16384-point transforms.  So CTA r of a pair computes just ITS output
 // of every stride-16384 butterfly while loading -- r = 0 the sums, r = 1 the twiddled differences -- then stages 13..10 on its 16 rows of
 // the 32 x 1024 view, two columns per thread, and the remaining two windows in its own shared memory.  Both CTAs read the whole input
 // (the second reader hits L2; HBM traffic stays the algorithmic 16 bytes per residue), nothing crosses SMs, no cluster barrier and no
 // MEMBAR; the multiplications are the same in total (CTA 1 does the 16384 of stage 14, CTA 0 none).
-template <int LOGE, bool LAZY>
-__global__ void __launch_bounds__(512, 2)
+template <int LOGN, int LOGE, bool LAZY>
+__global__ void __launch_bounds__(1 << (LOGN - 6), 1024 >> (LOGN - 6))
 k_crt_pow2_inv_h2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
-    constexpr int LOGN = 15, E = 1 << LOGE, G = 32;
-    static_assert(LOGE == 5, "half kernel: stage 14, a window of 4 stages, 2 windows of 5 stages");
+    // the transform as 32 rows x COLS columns; this CTA: rows 16 r .. 16 r + 15, every column, two columns per thread
+    constexpr int E = 1 << LOGE, G = 32, S2 = LOGN - 5, COLS = 1 << S2, T = COLS / 2, LB0 = ab_pow2_lb0(LOGN, LOGE, 2), KOFF = LB0 ? (1 << LB0) : 0;
+    static_assert(LOGE == 5 && LOGN >= 14 && LOGN <= 15, "half kernel: top stage, a window of up to 4 stages, 2 windows of 5 stages");
     extern __shared__ uint32_t sm[];
     const unsigned r = blockIdx.x & 1;
     const int tl = threadIdx.x, wb = tl / G, lg = tl % G;
@@ -349,34 +350,34 @@ k_crt_pow2_inv_h2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     const uint32_t q = lp.q;
     const uint2 *__restrict__ tw = lp.tw;
     int64_t *yp = y + (b * args.nlimbs + blockIdx.y) * (1 << LOGN);
-    pow2_c2_prefetch(args, y);
+    pow2_c2_prefetch<LOGN>(args, y);
     {
         constexpr int64_t base2 = ab_pow2_base(LOGN, LOGE, 2);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int col = tl + 512 * c;
+            const int col = tl + T * c;
             uint32_t lo[16], hi[16], x16[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                lo[i] = (uint32_t)__ldcs(yp + col + (i << 10));
-                hi[i] = (uint32_t)__ldcs(yp + col + ((i + 16) << 10));
+                lo[i] = (uint32_t)__ldcs(yp + col + (i << S2));
+                hi[i] = (uint32_t)__ldcs(yp + col + ((i + 16) << S2));
             }
             if (r == 0) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) x16[i] = LAZY ? ab_csub(lo[i] + hi[i], 2 * q) : ab_addmod(lo[i], hi[i], q);
             } else {
-                // twiddle k = 16 + i of window 2 for this column: entries (k >> 1) << 10 of the packed table, two per 16-byte load
+                // twiddle k = 16 + i (- KOFF) of window 2 for this column: entries (k >> 1) << S2 of the packed table, two per 16-byte load
                 const uint4 *tp = reinterpret_cast<const uint4 *>(tw + base2) + col;
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const uint4 pr = __ldg(tp + ((int64_t)((16 + i) >> 1) << 10));
+                    const uint4 pr = __ldg(tp + ((int64_t)((16 + i - KOFF) >> 1) << S2));
                     x16[i] = LAZY ? ab_shoup_lazy(lo[i] - hi[i] + 2 * q, pr.x, pr.y, q) : ab_shoup(ab_submod(lo[i], hi[i], q), pr.x, pr.y, q);
                     x16[i + 1] = LAZY ? ab_shoup_lazy(lo[i + 1] - hi[i + 1] + 2 * q, pr.z, pr.w, q) : ab_shoup(ab_submod(lo[i + 1], hi[i + 1], q), pr.z, pr.w, q);
                 }
             }
-            inv_window<4, 2, 10, 0, LAZY>(x16, lp, tw, base2, col, q);      // stages 13 .. 10: the first 16 twiddles of window 2
+            inv_window<4, 2, S2, LB0, LAZY>(x16, lp, tw, base2, col, q);      // the other stages of window 2: its first 16 twiddles
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sm[phys(i * 1024 + col)] = x16[i];
+            for (int i = 0; i < 16; ++i) sm[phys(i * COLS + col)] = x16[i];
         }
     }
     __syncthreads();
@@ -395,7 +396,7 @@ k_crt_pow2_inv_h2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     }
     __syncwarp();
     {
-        int4 *dst = reinterpret_cast<int4 *>(yp + (int64_t)(16 * r + wb) * G * E);
+        int4 *dst = reinterpret_cast<int4 *>(yp + (int64_t)((T / G) * r + wb) * G * E);
 #pragma unroll
         for (int j = 0; j < E / 2; ++j) {
             const int a = wb * G * E + 2 * (lg + j * G);
@@ -414,6 +415,11 @@ static int resident_ctas(K kernel, int threads, size_t smem) {
     return nb < 1 ? 1 : nb;
 }
 
+static bool pow2_split14() {      // n = 16384 inverse as two independent half-transform CTAs too: 0.693 -> 0.720 of the HBM roofline (AB_POW2_SPLIT14=0: one CTA)
+    static const bool on = !(getenv("AB_POW2_SPLIT14") && atoi(getenv("AB_POW2_SPLIT14")) == 0);
+    return on;
+}
+
 template <int LOGN, int LOGE, bool LAZY>
 static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool inverse, cudaStream_t st) {
     using C = Pow2Cfg<LOGN, LOGE>;
@@ -429,12 +435,23 @@ static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool 
         static thread_local bool ready = false;
         if (!ready) {
             AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_fwd_c2<LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
-            AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_inv_h2<LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
+            AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_inv_h2<LOGN, LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
             ready = true;
         }
         const dim3 g2((unsigned)(2 * args.batch), (unsigned)args.nlimbs);
-        if (inverse) k_crt_pow2_inv_h2<LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
+        if (inverse) k_crt_pow2_inv_h2<LOGN, LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
         else k_crt_pow2_fwd_c2<LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
+    } else if (inverse && LOGN == 14 && pow2_split14()) {
+        if constexpr (LOGN == 14) {
+            constexpr size_t half = ((size_t)(1 << 13) + (1 << 8)) * sizeof(uint32_t);
+            static thread_local bool ready = false;
+            if (!ready) {
+                AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_inv_h2<LOGN, LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
+                ready = true;
+            }
+            pa.pf_dist = (int32_t)(pf_waves * p->sm_count * 4);
+            k_crt_pow2_inv_h2<LOGN, LOGE, LAZY><<<dim3((unsigned)(2 * args.batch), (unsigned)args.nlimbs), 256, half, st>>>(pa, y);
+        }
     } else if (inverse) {
         auto k = k_crt_pow2_inv<LOGN, LOGE, LAZY>;
         static thread_local bool ready = false;

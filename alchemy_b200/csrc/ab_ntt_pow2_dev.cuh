@@ -20,14 +20,15 @@ struct Pow2Args {
     int32_t pf_dist;          // cluster kernels: CTAs ahead (in launch order) whose input is pulled into L2; 0 = no prefetch
 };
 
-// 2-CTA cluster kernels (n = 32768): the half-transform that the CTA `dist` places later in launch order will load (128 KB, contiguous)
-// is requested into L2 now, 8 KB per thread of the first half-warp, so that its load phase waits on L2 instead of HBM
+// kernels with two CTAs per transform (n = 32768; the split inverse of n = 16384): the half-transform of the CTA `dist` places later in launch
+// order (contiguous) is requested into L2 now, 8 KB per thread of the first threads, so that its load phase waits on L2 instead of HBM
+template <int LOGN>
 __device__ __forceinline__ void pow2_c2_prefetch(const Pow2Args &args, const int64_t *y) {
-    if (args.pf_dist <= 0 || threadIdx.x >= 16) return;
+    if (args.pf_dist <= 0 || threadIdx.x >= (1 << (LOGN - 11))) return;
     const int64_t lin = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + args.pf_dist;
     if (lin >= (int64_t)gridDim.x * gridDim.y) return;
     const int64_t x2 = lin % gridDim.x, l2 = lin / gridDim.x;
-    const int64_t *src = y + ((x2 >> 1) * args.nlimbs + l2) * (1 << 15) + (x2 & 1) * (1 << 14) + threadIdx.x * 1024;
+    const int64_t *src = y + ((x2 >> 1) * args.nlimbs + l2) * (1 << LOGN) + (x2 & 1) * (1 << (LOGN - 1)) + threadIdx.x * 1024;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(8192) : "memory");
 }
 // the same for the one-transform-per-CTA kernels (n = 8192, 16384): the transform of the CTA `dist` places later, 8 KB per thread
