@@ -329,7 +329,7 @@ k_crt_pow2_fwd_c2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y
     }
 }
 
-// n = 32768 (and n = 16384) inverse as two independent CTAs per transform, WITHOUT a cluster (round 2; the 2-CTA cluster version it replaces pushed half of the first window's outputs into the
+// n = 32768 (and n = 16384, 8192) inverse as two independent CTAs per transform, WITHOUT a cluster (round 2; the 2-CTA cluster version it replaces pushed half of the first window's outputs into the
 // peer's shared memory and measured 0.566 ms per 2.147 GB launch against 0.515 ms here): the first stage of the inverse (stride 16384, one twiddle per butterfly) is the only one that
 // crosses the halves, and after it the two halves are independent 16384-point transforms.  So CTA r of a pair computes just ITS output
 // of every stride-16384 butterfly while loading -- r = 0 the sums, r = 1 the twiddled differences -- then stages 13..10 on its 16 rows of
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 6), 1024 >> (LOGN - 6))
 k_crt_pow2_inv_h2(const __grid_constant__ Pow2Args args, int64_t *__restrict__ y) {
     // the transform as 32 rows x COLS columns; this CTA: rows 16 r .. 16 r + 15, every column, two columns per thread
     constexpr int E = 1 << LOGE, G = 32, S2 = LOGN - 5, COLS = 1 << S2, T = COLS / 2, LB0 = ab_pow2_lb0(LOGN, LOGE, 2), KOFF = LB0 ? (1 << LB0) : 0;
-    static_assert(LOGE == 5 && LOGN >= 14 && LOGN <= 15, "half kernel: top stage, a window of up to 4 stages, 2 windows of 5 stages");
+    static_assert(LOGE == 5 && LOGN >= 13 && LOGN <= 15, "half kernel: top stage, a window of up to 4 stages, 2 windows of 5 stages");
     extern __shared__ uint32_t sm[];
     const unsigned r = blockIdx.x & 1;
     const int tl = threadIdx.x, wb = tl / G, lg = tl % G;
@@ -415,8 +415,8 @@ static int resident_ctas(K kernel, int threads, size_t smem) {
     return nb < 1 ? 1 : nb;
 }
 
-static bool pow2_split14() {      // n = 16384 inverse as two independent half-transform CTAs too: 0.693 -> 0.720 of the HBM roofline (AB_POW2_SPLIT14=0: one CTA)
-    static const bool on = !(getenv("AB_POW2_SPLIT14") && atoi(getenv("AB_POW2_SPLIT14")) == 0);
+static bool pow2_split() {      // n = 8192 and 16384 inverse as two independent half-transform CTAs too: 0.775 -> 0.810 and 0.693 -> 0.720 of the HBM
+    static const bool on = !(getenv("AB_POW2_SPLIT") && atoi(getenv("AB_POW2_SPLIT")) == 0);      // roofline (AB_POW2_SPLIT=0: one CTA per transform)
     return on;
 }
 
@@ -441,16 +441,16 @@ static void launch_one(const ab_plan *p, const Pow2Args &args, int64_t *y, bool 
         const dim3 g2((unsigned)(2 * args.batch), (unsigned)args.nlimbs);
         if (inverse) k_crt_pow2_inv_h2<LOGN, LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
         else k_crt_pow2_fwd_c2<LOGE, LAZY><<<g2, 512, half, st>>>(pa, y);
-    } else if (inverse && LOGN == 14 && pow2_split14()) {
-        if constexpr (LOGN == 14) {
-            constexpr size_t half = ((size_t)(1 << 13) + (1 << 8)) * sizeof(uint32_t);
+    } else if (inverse && (LOGN == 14 || LOGN == 13) && pow2_split()) {
+        if constexpr (LOGN == 14 || LOGN == 13) {
+            constexpr size_t half = ((size_t)(1 << (LOGN - 1)) + (1 << (LOGN - 6))) * sizeof(uint32_t);
             static thread_local bool ready = false;
             if (!ready) {
                 AB_CHECK_CUDA(cudaFuncSetAttribute(k_crt_pow2_inv_h2<LOGN, LOGE, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)half));
                 ready = true;
             }
-            pa.pf_dist = (int32_t)(pf_waves * p->sm_count * 4);
-            k_crt_pow2_inv_h2<LOGN, LOGE, LAZY><<<dim3((unsigned)(2 * args.batch), (unsigned)args.nlimbs), 256, half, st>>>(pa, y);
+            pa.pf_dist = (int32_t)(pf_waves * p->sm_count * (1024 >> (LOGN - 6)));
+            k_crt_pow2_inv_h2<LOGN, LOGE, LAZY><<<dim3((unsigned)(2 * args.batch), (unsigned)args.nlimbs), 1 << (LOGN - 6), half, st>>>(pa, y);
         }
     } else if (inverse) {
         auto k = k_crt_pow2_inv<LOGN, LOGE, LAZY>;

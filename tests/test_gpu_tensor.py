@@ -248,3 +248,19 @@ def test_host_entry_interleaved_tuples():
     assert (host.transpose(0, 2, 1) == oracle_limbs(O.crt, m, moduli, x)).all()
     ab.GT.hostOp(plan, "crt_inv", host)
     assert (host.transpose(0, 2, 1) == x).all()
+
+
+@pytest.mark.parametrize("switch", ["AB_POW2_SPLIT=0", "AB_POW2_PF_WAVES=0", "AB_POW2_PF_WAVES=1.5"])
+def test_power_of_two_kernel_variants_compute_the_same_bits(switch):
+    """the large power-of-two inverses run as two independent half-transform CTAs and every large kernel prefetches a later CTA's input
+    into L2; the one-CTA inverse kernels and other prefetch distances must give the same bits (switches are read once per process)"""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    k, v = switch.split("=")
+    env[k] = v
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                          "test_crt_and_inverse_match_oracle and (8192 or 16384 or 32768 or 65536)", "-p", "no:cacheprovider"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
