@@ -385,7 +385,7 @@ def main():
                                                  "l2": "in-place buffer of %.0f MB per GPU, larger than the 126 MB L2" % (batch * L * n * 8 / 1e6),
                                                  "step": "1 CRT launch + 1 crtInv launch over the whole batch"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(m, L, batch),
-                             "peak_source": peak_src, "kernel": ("k_crt_pow2_fwd_c2 / k_crt_pow2_inv_c2 (2-CTA clusters)" if n == 32768 else "k_crt_pow2_fwd / k_crt_pow2_inv") if not args.m else "k_crt_mixed",
+                             "peak_source": peak_src, "kernel": ("k_crt_pow2_fwd_c2 (2-CTA cluster) / k_crt_pow2_inv_h2 (two independent half-transform CTAs)" if n == 32768 else "k_crt_pow2_fwd / k_crt_pow2_inv") if not args.m else "k_crt_mixed",
                              "bytes_per_launch": bytes_per_launch, "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                              "fwd_gbs": bytes_per_launch / (fwd_ms * 1e-3) / 1e9, "inv_gbs": bytes_per_launch / (inv_ms * 1e-3) / 1e9},
                 "gpu_launches": int(launches), "clocks": clocks}
