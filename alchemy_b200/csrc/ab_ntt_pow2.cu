@@ -18,8 +18,12 @@
 // NEXT transform's int64 residues are streamed into it with 4-byte cp.async (LDGSTS) while the last
 // window's butterflies run and its results are stored: HBM reads, HBM writes and arithmetic overlap
 // inside one CTA even at n = 32768 where only one CTA fits an SM.
+// Round 2: from n = 8192 up the first threads of a CTA request the input of a CTA a quarter of a resident wave later into L2
+// (cp.async.bulk.prefetch.L2), and the inverses at n = 8192 ... 32768 run as TWO independent CTAs per transform (k_crt_pow2_inv_h2: the
+// first inverse stage is the only one that crosses the halves; each CTA computes its own output of it while loading).  The forward at
+// n = 32768 is a 2-CTA cluster (its cross-half stage is the last one, so it needs the exchange over DSMEM).
 // HBM traffic is one read and one write of the int64 residues: 16 n bytes per transform, the
-// algorithmic minimum.  Twiddles (Shoup pairs) are window-packed so one 16-byte load fetches two;
+// algorithmic minimum (the split inverses read the input twice, the second time mostly from L2: +7.5 % DRAM reads at n = 32768).  Twiddles (Shoup pairs) are window-packed so one 16-byte load fetches two;
 // window 0's 31 twiddles are the same for every thread and travel as kernel constants.
 #include "ab_internal.h"
 #include <cooperative_groups.h>
